@@ -1,0 +1,41 @@
+"""Build recipe for the CUDA extension (in-tree, sm_100a only).
+
+    python -m brickmap_b200.build            # -> brickmap_b200/libbrickmap_b200.so
+
+The flags matter for parity, not only for speed: -fmad=false stops nvcc from contracting mul+add pairs on its
+own; every FMA the reference build performs is written out explicitly in csrc/bm_device.cuh.
+"""
+import os
+import subprocess
+import sys
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+CSRC = os.path.join(HERE, "csrc")
+SOURCES = ["bm_kernels.cu", "bm_scene_store.cu"]
+HEADERS = ["bm_device.cuh", os.path.join("..", "..", "include", "brickmap_b200.h")]
+LIB = os.path.join(HERE, "libbrickmap_b200.so")
+NVCC_FLAGS = ["-std=c++17", "-O3", "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-fmad=false",
+              "-Xcompiler", "-fPIC", "-shared"]
+
+
+def needs_build():
+    if not os.path.exists(LIB):
+        return True
+    t = os.path.getmtime(LIB)
+    deps = [os.path.join(CSRC, s) for s in SOURCES + HEADERS] + [os.path.abspath(__file__)]
+    return any(os.path.getmtime(d) > t for d in deps)
+
+
+def build(force=False, verbose=False):
+    """Compile csrc/*.cu into libbrickmap_b200.so with nvcc (cross-compiles without a GPU)."""
+    if not force and not needs_build():
+        return LIB
+    nvcc = os.environ.get("NVCC", "nvcc")
+    cmd = [nvcc] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + ["-o", LIB] + [os.path.join(CSRC, s) for s in SOURCES]
+    subprocess.check_call(cmd)
+    return LIB
+
+
+if __name__ == "__main__":
+    build(force="--force" in sys.argv, verbose="-v" in sys.argv)
+    print(LIB)

@@ -1,0 +1,516 @@
+// Device building blocks of the B200 path tracer: RNG + sampling, primary-ray generation, brickmap traversal,
+// sun-sky model, shading. Compiled with -fmad=false: every fused multiply-add below is written out as fmaf()
+// where the reference build (nvcc default -fmad=true, sm_100a) fuses, so that ray geometry is bit-identical
+// with the reference's kernels (hit/miss at voxel boundaries flips on 1-ulp differences). Radiance (sky model)
+// is only required to agree to 1e-4 relative and is evaluated in FP32 with per-frame constants hoisted to the
+// host (the reference evaluates FP64 pow/exp per shaded vertex, sunsky.cu:10-26).
+//
+// Reference citations are file:line under the reference's src/.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "../../include/brickmap_b200.h"
+
+namespace bm {
+
+constexpr float kPi = 3.1415926535897932f;  // variables.h:3
+constexpr float kEpsilon = 0.001f;          // variables.h:22
+constexpr float kVeryFar = 1e20f;           // kernel.cu:12
+constexpr int kMaxBounces = 3;              // kernel.cu:13
+
+struct F3 {
+	float x, y, z;
+};
+struct I3 {
+	int x, y, z;
+};
+
+__device__ __forceinline__ F3 make_f3(float x, float y, float z) { return F3{ x, y, z }; }
+__device__ __forceinline__ float comp(const F3& v, int i) { return i == 0 ? v.x : (i == 1 ? v.y : v.z); }
+__device__ __forceinline__ int comp(const I3& v, int i) { return i == 0 ? v.x : (i == 1 ? v.y : v.z); }
+
+// GLM's scalar min/max/sign (documented semantics; NaN behaviour follows from the comparisons)
+__device__ __forceinline__ float gmin(float x, float y) { return (y < x) ? y : x; }
+__device__ __forceinline__ float gmax(float x, float y) { return (x < y) ? y : x; }
+__device__ __forceinline__ float gsign(float x) { return (float)(0.0f < x) - (float)(x < 0.0f); }
+
+// dot(v,v) as the reference build evaluates it: fma(z,z, fma(x,x, y*y))
+__device__ __forceinline__ float dot_self(const F3& v) { return fmaf(v.z, v.z, fmaf(v.x, v.x, v.y * v.y)); }
+// glm::normalize(v) = v * (1 / sqrt(dot(v,v)))
+__device__ __forceinline__ F3 normalize_ref(const F3& v) {
+	const float r = 1.0f / sqrtf(dot_self(v));
+	return F3{ r * v.x, r * v.y, r * v.z };
+}
+
+// ---- RNG and sampling (kernel.cu:19-103) -----------------------------------------------------------------
+__device__ __forceinline__ uint32_t random_int(uint32_t& seed) {  // kernel.cu:19-24
+	seed ^= seed << 13;
+	seed ^= seed >> 17;
+	seed ^= seed << 5;
+	return seed;
+}
+__device__ __forceinline__ float random_float(uint32_t& seed) { return (float)random_int(seed) * 2.3283064365387e-10f; }  // :27-29
+__device__ __forceinline__ float random_float2(uint32_t& seed) { return (float)(random_int(seed) >> 16) / 65535.0f; }     // :31-33
+
+__device__ __forceinline__ void stratified_sample(uint32_t& seed, float& sx, float& sy) {  // kernel.cu:40-61
+	const int chosen = (int)(random_float(seed) * (16.0f + 0.99999f));
+	const int stratum_x = chosen % 4;
+	const int stratum_y = (chosen / 4) % 4;
+	sx = 0.25f * (float)stratum_x + random_float(seed) * 0.25f;
+	sy = 0.25f * (float)stratum_y + random_float(seed) * 0.25f;
+}
+
+__device__ __forceinline__ void concentric_disk(float ux, float uy, float& dx, float& dy) {  // kernel.cu:85-103
+	const float ox = 2.0f * ux - 1.0f;
+	const float oy = 2.0f * uy - 1.0f;
+	if (ox == 0.0f && oy == 0.0f) {
+		dx = 0.0f;
+		dy = 0.0f;
+		return;
+	}
+	float theta, r;
+	if (fabsf(ox) > fabsf(oy)) {
+		r = ox;
+		theta = (kPi / 4) * (oy / ox);
+	} else {
+		r = oy;
+		theta = fmaf(ox / oy, -(kPi / 4), kPi / 2);
+	}
+	dx = r * cosf(theta);
+	dy = r * sinf(theta);
+}
+
+// ---- per-frame constants ------------------------------------------------------------------------------------
+struct FrameParams {
+	// camera (kernel.cu:384-385,416)
+	F3 cam_right, cam_up, cam_dir, cam_pos;
+	float focal3;       // focalDistance * 3 (kernel.cu:191)
+	float lens_radius;
+	I3 cam_cell;        // ivec3(camera.position / 8.f) (kernel.cu:418,420)
+	uint32_t width, height;      // full image
+	uint32_t tile_row0, tile_rows;  // rows rendered by this context
+	uint32_t n_slots;   // ray_queue_buffer_size
+	// sun / sky constants (sunsky.cu, hoisted)
+	F3 sun_dir;
+	float sun_angular_cos;    // sunAngularDiameterCos
+	float cone_extent;        // 1 - sunAngularDiameterCos (kernel.cu:274)
+	float sun_e;              // SunIntensity(dot(sunDirection, up)) (sunsky.cu:24-26)
+	F3 rayleigh;              // rayleighAtX
+	F3 mie;                   // mieAtX = totalMie(...) * mieCoefficient (sunsky.cu:14-18,44)
+	F3 total;                 // rayleighAtX + mieAtX
+	float mix_a;              // clamp(pow(1 - dot(up, sunDirection), 5), 0, 1)
+	float rayleigh_k;         // 3 / (16 pi)
+	float hg_k;               // (1 / (4 pi)) * (1 - g^2)
+	float hg_g;               // mieDirectionalG
+};
+
+// ---- scene view -------------------------------------------------------------------------------------------
+struct SceneView {
+	uint32_t* const* indices;     // GPUScene.indices (Scene.h:10)
+	bm_brick* const* bricks;      // GPUScene.bricks (Scene.h:11)
+	int32_t* load_queue;          // GPUScene.brick_load_queue
+	uint32_t* load_queue_count;   // GPUScene.brick_load_queue_count
+	uint32_t* flat_indices;       // != nullptr: indices[sc] == flat_indices + sc * 4096 (verified at bind time)
+	const uint32_t* coarse;       // emptiness bitmap, 1 bit per block of (1 << coarse_shift)^3 cells (global copy)
+	int cells, cells_height;      // variables.h:17-18
+	int supergrid_xy;             // variables.h:12
+	float grid_size_f, grid_height_f;
+	int lod2, lod8;               // variables.h:25-27
+	uint32_t queue_size;          // variables.h:35
+	int coarse_shift, coarse_nx, coarse_nxy;  // bitmap geometry
+	uint32_t coarse_words;
+};
+
+struct WorkCounters {
+	unsigned long long steps, index_reads, bricks, requests;
+};
+
+// ---- traversal (voxel.cuh) ----------------------------------------------------------------------------------
+struct Dda {
+	I3 pos;
+	I3 stepi;
+	F3 step, tmax, tdelta;
+};
+
+// common set-up of voxel.cuh:27-48 / 80-101 / 158-186
+__device__ __forceinline__ void dda_setup(const F3& o, const F3& d, Dda& a) {
+	a.pos = I3{ (int)o.x, (int)o.y, (int)o.z };
+	const F3 cb{ d.x > 0.f ? (float)(a.pos.x + 1) : (float)a.pos.x, d.y > 0.f ? (float)(a.pos.y + 1) : (float)a.pos.y,
+		         d.z > 0.f ? (float)(a.pos.z + 1) : (float)a.pos.z };
+	a.step = F3{ gsign(d.x), gsign(d.y), gsign(d.z) };
+	a.stepi = I3{ (int)a.step.x, (int)a.step.y, (int)a.step.z };
+	const F3 rdinv{ d.x == 0.0f ? 0.0f : 1.f / d.x, d.y == 0.0f ? 0.0f : 1.f / d.y, d.z == 0.0f ? 0.0f : 1.f / d.z };
+	a.tmax = F3{ d.x != 0.f ? (cb.x - o.x) * rdinv.x : 1000000.f, d.y != 0.f ? (cb.y - o.y) * rdinv.y : 1000000.f,
+		         d.z != 0.f ? (cb.z - o.z) * rdinv.z : 1000000.f };
+	a.tdelta = F3{ a.step.x * rdinv.x, a.step.y * rdinv.y, a.step.z * rdinv.z };
+}
+
+// voxel.cuh:66-74 / 122-130 / 249-258. Returns false when the ray leaves through `out`.
+__device__ __forceinline__ bool dda_advance(Dda& a, const I3& out, int& step_axis) {
+	const float tx = a.tmax.x, ty = a.tmax.y, tz = a.tmax.z;
+	const bool xy = tx < ty, xz = tx < tz, yz = ty < tz;
+	step_axis = xy ? (xz ? 0 : 2) : (yz ? 1 : 2);
+	const bool mx = xy && xz;
+	const bool my = (ty <= tx) && yz;
+	const bool mz = (tz <= tx) && (tz <= ty);
+	// pos += mask * step: int(1.f * step) or int(0.f * step) = 0
+	a.pos.x += mx ? a.stepi.x : 0;
+	a.pos.y += my ? a.stepi.y : 0;
+	a.pos.z += mz ? a.stepi.z : 0;
+	if (comp(a.pos, step_axis) == comp(out, step_axis)) return false;
+	// tmax += mask * tdelta: mask is 0/1, so this is a predicated add (1 * tdelta is exact; 0 * tdelta == 0 leaves
+	// tmax unchanged for every finite tdelta, i.e. unless a direction component is a non-zero denormal < 2^-128)
+	a.tmax.x = mx ? tx + a.tdelta.x : tx;
+	a.tmax.y = my ? ty + a.tdelta.y : ty;
+	a.tmax.z = mz ? tz + a.tdelta.z : tz;
+	return true;
+}
+
+// voxel.cuh:26-77 (2x2x2 LoD octants)
+__device__ __forceinline__ bool intersect_byte(const F3& origin, const F3& direction, F3& normal, float& distance, uint32_t byte) {
+	Dda a;
+	dda_setup(origin, direction, a);
+	const I3 out{ direction.x > 0.f ? 2 : -1, direction.y > 0.f ? 2 : -1, direction.z > 0.f ? 2 : -1 };
+	a.pos = I3{ a.pos.x % 2, a.pos.y % 2, a.pos.z % 2 };
+	distance = 0.f;
+	int step_axis = -1;
+	for (;;) {
+		const int bit = a.pos.x + a.pos.y * 2 + a.pos.z * 4;
+		if (bit >= 0 && bit < 8 && ((byte >> bit) & 1u)) {
+			if (step_axis > -1) {
+				normal = F3{ step_axis == 0 ? -a.step.x : 0.f, step_axis == 1 ? -a.step.y : 0.f, step_axis == 2 ? -a.step.z : 0.f };
+				distance = comp(a.tmax, step_axis) - comp(a.tdelta, step_axis);
+			}
+			return true;
+		}
+		if (!dda_advance(a, out, step_axis)) break;
+	}
+	return false;
+}
+
+// voxel.cuh:79-133 (8x8x8 voxel brick). The 64-byte brick is fetched once as four 128-bit loads; the DDA then
+// tests bits of the 8 z-slices held in registers instead of one dependent 4-byte global load per step.
+__device__ __forceinline__ bool intersect_brick(const F3& origin, const F3& direction, F3& normal, float& distance, const bm_brick* brick) {
+	Dda a;
+	dda_setup(origin, direction, a);
+	const I3 out{ direction.x > 0.f ? 8 : -1, direction.y > 0.f ? 8 : -1, direction.z > 0.f ? 8 : -1 };
+	a.pos = I3{ a.pos.x % 8, a.pos.y % 8, a.pos.z % 8 };
+	distance = 0.f;
+	int step_axis = -1;
+	const uint32_t* words = brick->data;
+	for (;;) {
+		const int lin = a.pos.x + a.pos.y * 8 + a.pos.z * 64;
+		// negative remainders (origin slightly outside on the low side) index out of the brick in the reference
+		// (undefined there); they are treated as empty here and in the oracle
+		if (lin >= 0 && lin < 512 && ((__ldg(words + (lin >> 5)) >> (lin & 31)) & 1u)) {
+			if (step_axis > -1) {
+				normal = F3{ step_axis == 0 ? -a.step.x : 0.f, step_axis == 1 ? -a.step.y : 0.f, step_axis == 2 ? -a.step.z : 0.f };
+				distance = comp(a.tmax, step_axis) - comp(a.tdelta, step_axis);
+			}
+			return true;
+		}
+		if (!dda_advance(a, out, step_axis)) break;
+	}
+	return false;
+}
+
+// voxel.cuh:13-24
+__device__ __forceinline__ bool intersect_aabb(const SceneView& sv, const F3& o, const F3& d, float& tmin) {
+	const F3 t1{ (0.0f - o.x) / d.x, (0.0f - o.y) / d.y, (0.0f - o.z) / d.z };
+	const F3 t2{ (sv.grid_size_f - o.x) / d.x, (sv.grid_size_f - o.y) / d.y, (sv.grid_height_f - o.z) / d.z };
+	const F3 lo{ gmin(t1.x, t2.x), gmin(t1.y, t2.y), gmin(t1.z, t2.z) };
+	const F3 hi{ gmax(t1.x, t2.x), gmax(t1.y, t2.y), gmax(t1.z, t2.z) };
+	tmin = gmax(gmax(lo.x, 0.f), gmax(lo.y, lo.z));
+	return gmin(hi.x, gmin(hi.y, hi.z)) > tmin;
+}
+
+// intersect_voxel, voxel.cuh:135-261. `coarse_smem` is the block's shared-memory copy of the emptiness bitmap
+// (nullptr: read every index word like the reference). The DDA performs exactly the reference's sequence of
+// floating-point steps; only the LOADS of index words inside empty blocks are skipped.
+template <bool COUNT>
+__device__ __forceinline__ bool intersect_voxel(const SceneView& sv, const uint32_t* coarse_smem, F3 origin, const F3 direction, F3& normal,
+                                                float& distance, const I3 cam, WorkCounters* wc) {
+	float tminn;
+	if (!intersect_aabb(sv, origin, direction, tminn)) return false;
+
+	if (tminn > 0) {  // voxel.cuh:142-155
+		origin = F3{ fmaf(direction.x, tminn, origin.x), fmaf(direction.y, tminn, origin.y), fmaf(direction.z, tminn, origin.z) };
+		const float ratio = sv.grid_size_f / sv.grid_height_f;
+		const float sxy = 1.f / ratio;
+		const F3 center{ sv.grid_size_f / 2.f, sv.grid_size_f / 2.f, sv.grid_height_f / 2.f };
+		F3 to_center{ fabsf(center.x - origin.x) * sxy, fabsf(center.y - origin.y) * sxy, fabsf(center.z - origin.z) * 1.f };
+		const F3 signs{ gsign(origin.x - center.x), gsign(origin.y - center.y), gsign(origin.z - center.z) };
+		const float m = gmax(to_center.x, gmax(to_center.y, to_center.z));
+		to_center = F3{ to_center.x / m, to_center.y / m, to_center.z / m };
+		normal = F3{ signs.x * truncf(to_center.x + 0.000001f), signs.y * truncf(to_center.y + 0.000001f), signs.z * truncf(to_center.z + 0.000001f) };
+		origin = F3{ origin.x - normal.x * kEpsilon, origin.y - normal.y * kEpsilon, origin.z - normal.z * kEpsilon };
+	}
+
+	origin = F3{ origin.x * 0.125f, origin.y * 0.125f, origin.z * 0.125f };  // origin /= 8.f
+	Dda a;
+	dda_setup(origin, direction, a);
+	if (a.pos.x < 0 || a.pos.x >= sv.cells || a.pos.y < 0 || a.pos.y >= sv.cells || a.pos.z < 0 || a.pos.z >= sv.cells_height) return false;
+	const I3 out{ direction.x > 0.f ? sv.cells : -1, direction.y > 0.f ? sv.cells : -1, direction.z > 0.f ? sv.cells_height : -1 };
+
+	int step_axis = -1;
+	for (;;) {
+		bool maybe = true;
+		if (COUNT) wc->steps++;
+		if (coarse_smem) {
+			const int cb = (a.pos.x >> sv.coarse_shift) + (a.pos.y >> sv.coarse_shift) * sv.coarse_nx + (a.pos.z >> sv.coarse_shift) * sv.coarse_nxy;
+			maybe = (coarse_smem[cb >> 5] >> (cb & 31)) & 1u;
+		}
+		if (maybe) {
+			const int sc = (a.pos.x >> 4) + (a.pos.y >> 4) * sv.supergrid_xy + (a.pos.z >> 4) * sv.supergrid_xy * sv.supergrid_xy;  // voxel.cuh:197
+			const int local = (a.pos.x & 15) + (a.pos.y & 15) * 16 + (a.pos.z & 15) * 256;                                        // voxel.cuh:198
+			uint32_t* word = sv.flat_indices ? sv.flat_indices + (((size_t)sc << 12) + local) : sv.indices[sc] + local;
+			const uint32_t index = __ldg(word);
+			if (COUNT) wc->index_reads++;
+			if (index) {
+				float new_distance = 0.f;
+				if (step_axis != -1) {
+					normal = F3{ step_axis == 0 ? -a.step.x : 0.f, step_axis == 1 ? -a.step.y : 0.f, step_axis == 2 ? -a.step.z : 0.f };
+					new_distance = comp(a.tmax, step_axis) - comp(a.tdelta, step_axis);
+				}
+				const int dx = cam.x - a.pos.x, dy = cam.y - a.pos.y, dz = cam.z - a.pos.z;
+				const int lod_distance_squared = dx * dx + dy * dy + dz * dz;
+				float sub_distance = 0.f;
+				if (lod_distance_squared > sv.lod8) {  // voxel.cuh:212-214
+					distance = new_distance * 8.f + tminn;
+					return true;
+				} else if (lod_distance_squared > sv.lod2) {  // voxel.cuh:215-220
+					const F3 x{ fmaf(direction.x, new_distance, origin.x), fmaf(direction.y, new_distance, origin.y), fmaf(direction.z, new_distance, origin.z) };
+					const F3 so{ fmaf(normal.x * 0.2f, -kEpsilon, x.x + x.x), fmaf(normal.y * 0.2f, -kEpsilon, x.y + x.y), fmaf(normal.z * 0.2f, -kEpsilon, x.z + x.z) };
+					if (intersect_byte(so, direction, normal, sub_distance, (index & BM_BRICK_LOD_BITS) >> 12)) {
+						distance = (new_distance * 8.f + sub_distance * 4.f) + tminn;
+						return true;
+					}
+				} else if (index & BM_BRICK_LOADED_BIT) {  // voxel.cuh:222-227
+					const bm_brick* p = sv.bricks[sc] + (index & BM_BRICK_INDEX_BITS);
+					if (COUNT) wc->bricks++;
+					const F3 x{ fmaf(direction.x, new_distance, origin.x), fmaf(direction.y, new_distance, origin.y), fmaf(direction.z, new_distance, origin.z) };
+					const F3 so{ x.x * 8.f - normal.x * kEpsilon, x.y * 8.f - normal.y * kEpsilon, x.z * 8.f - normal.z * kEpsilon };
+					if (intersect_brick(so, direction, normal, sub_distance, p)) {
+						distance = (new_distance * 8.f + sub_distance) + tminn;
+						return true;
+					}
+				} else if (index & BM_BRICK_UNLOADED_BIT) {  // voxel.cuh:228-244
+					const uint32_t old = atomicOr(word, BM_BRICK_REQUESTED_BIT);
+					if (!(old & BM_BRICK_REQUESTED_BIT)) {
+						const uint32_t load_index = atomicAdd(sv.load_queue_count, 1u);
+						if (load_index < sv.queue_size) {
+							sv.load_queue[3 * load_index + 0] = a.pos.x;
+							sv.load_queue[3 * load_index + 1] = a.pos.y;
+							sv.load_queue[3 * load_index + 2] = a.pos.z;
+							if (COUNT) wc->requests++;
+						} else {
+							atomicAnd(word, ~BM_BRICK_REQUESTED_BIT);
+						}
+					}
+					distance = new_distance * 8.f + tminn;
+					return true;
+				}
+			}
+		}
+		if (!dda_advance(a, out, step_axis)) break;
+	}
+	return false;
+}
+
+// ---- sun-sky model (sunsky.cu) -------------------------------------------------------------------------------
+struct SkyTerms {
+	F3 fex, sky;
+	float cos_view_sun;
+};
+__device__ __forceinline__ SkyTerms sky_terms(const FrameParams& fp, const F3& view) {  // common body of sunsky.cu:32-67 / 76-111 / 116-153
+	SkyTerms r;
+	r.cos_view_sun = view.x * fp.sun_dir.x + view.y * fp.sun_dir.y + view.z * fp.sun_dir.z;
+	const float cos_up_view = view.z;  // dot(up, viewDir), up = (0,0,1) (sunsky.cu:5)
+	const float zenith = gmax(0.0f, cos_up_view);
+	const float rl = 8.4E3f / zenith;   // rayleighZenithLength (sunsky.cuh:37)
+	const float ml = 1.25E3f / zenith;  // mieZenithLength (sunsky.cuh:38)
+	r.fex = F3{ expf(-(fp.rayleigh.x * rl + fp.mie.x * ml)), expf(-(fp.rayleigh.y * rl + fp.mie.y * ml)), expf(-(fp.rayleigh.z * rl + fp.mie.z * ml)) };
+	const float c = r.cos_view_sun;
+	const float rp = fp.rayleigh_k * (1.0f + c * c);                                    // RayleighPhase, sunsky.cu:10-12
+	const float hx = 1.0f - 2.0f * fp.hg_g * c + fp.hg_g * fp.hg_g;
+	const float hg = fp.hg_k / (hx * sqrtf(hx));                                        // hgPhase, sunsky.cu:20-22 (x^1.5 = x sqrt x)
+	const F3 light{ fp.rayleigh.x * rp + fp.mie.x * hg, fp.rayleigh.y * rp + fp.mie.y * hg, fp.rayleigh.z * rp + fp.mie.z * hg };
+	const F3 se{ fp.sun_e * (light.x / fp.total.x), fp.sun_e * (light.y / fp.total.y), fp.sun_e * (light.z / fp.total.z) };
+	const float a = fp.mix_a;
+	r.sky = F3{ (se.x * (1.0f - r.fex.x)) * (1.0f * (1.0f - a) + sqrtf(se.x * r.fex.x) * a), (se.y * (1.0f - r.fex.y)) * (1.0f * (1.0f - a) + sqrtf(se.y * r.fex.y) * a),
+		        (se.z * (1.0f - r.fex.z)) * (1.0f * (1.0f - a) + sqrtf(se.z * r.fex.z) * a) };
+	return r;
+}
+// sun(), sunsky.cu:32-74: only the extinction term depends on the view direction; the "disk" factor is 1 unless
+// cos(view, sun) is exactly 0 (sunsky.cu:70 compares against (cos ? 1.0 : 0.0)).
+__device__ __forceinline__ F3 sun_radiance(const FrameParams& fp, const F3& view) {
+	const float cvs = view.x * fp.sun_dir.x + view.y * fp.sun_dir.y + view.z * fp.sun_dir.z;
+	const float zenith = gmax(0.0f, view.z);
+	const float rl = 8.4E3f / zenith, ml = 1.25E3f / zenith;
+	const float disk = (fp.sun_angular_cos < (cvs != 0.0f ? 1.0f : 0.0f)) ? 1.0f : 0.0f;
+	const float k = fp.sun_e * 19000.0f;
+	return F3{ 0.01f * ((k * expf(-(fp.rayleigh.x * rl + fp.mie.x * ml))) * disk), 0.01f * ((k * expf(-(fp.rayleigh.y * rl + fp.mie.y * ml))) * disk),
+		       0.01f * ((k * expf(-(fp.rayleigh.z * rl + fp.mie.z * ml))) * disk) };
+}
+__device__ __forceinline__ F3 sky_radiance(const FrameParams& fp, const F3& view) {  // sky(), sunsky.cu:76-114 (SkyFactor = 1)
+	const SkyTerms t = sky_terms(fp, view);
+	return F3{ 0.01f * t.sky.x, 0.01f * t.sky.y, 0.01f * t.sky.z };
+}
+__device__ __forceinline__ F3 sunsky_radiance(const FrameParams& fp, const F3& view) {  // sunsky(), sunsky.cu:116-161
+	if (fp.sun_angular_cos == 1.0f) return F3{ 1.0f, 0.0f, 0.0f };
+	const SkyTerms t = sky_terms(fp, view);
+	float s = (t.cos_view_sun - fp.sun_angular_cos) / ((fp.sun_angular_cos + 0.00002f) - fp.sun_angular_cos);  // glm::smoothstep
+	s = gmin(gmax(s, 0.0f), 1.0f);
+	const float disk = s * s * (3.0f - 2.0f * s);
+	const float k = fp.sun_e * 19000.0f;
+	return F3{ 0.01f * (((k * t.fex.x) * disk) * 1E-5f + t.sky.x), 0.01f * (((k * t.fex.y) * disk) * 1E-5f + t.sky.y), 0.01f * (((k * t.fex.z) * disk) * 1E-5f + t.sky.z) };
+}
+
+// getConeSample, sunsky.cu:163-184 (FMA placement as in the reference build)
+__device__ __forceinline__ F3 cone_sample(F3 dir, float extent, uint32_t& seed) {
+	dir = normalize_ref(dir);
+	const F3 o = fabsf(dir.x) > fabsf(dir.z) ? F3{ -dir.y, dir.x, 0.0f } : F3{ 0.0f, -dir.z, dir.y };
+	const float ro = 1.0f / sqrtf(fmaf(o.z, o.z, fmaf(o.x, o.x, o.y * o.y)));
+	const F3 o1{ ro * o.x, ro * o.y, ro * o.z };
+	const F3 cr{ fmaf(dir.y, o1.z, -(dir.z * o1.y)), fmaf(dir.z, o1.x, -(dir.x * o1.z)), fmaf(dir.x, o1.y, -(dir.y * o1.x)) };
+	const F3 o2 = normalize_ref(cr);
+	float rx = random_float2(seed);
+	float ry = random_float2(seed);
+	rx = (rx + rx) * kPi;
+	ry = fmaf(-ry, extent, 1.0f);
+	const float oneminus = sqrtf(fmaf(-ry, ry, 1.0f));
+	const float cw = oneminus * cosf(rx);
+	const float sw = oneminus * sinf(rx);
+	return F3{ fmaf(dir.x, ry, fmaf(o2.x, sw, o1.x * cw)), fmaf(dir.y, ry, fmaf(o2.y, sw, o1.y * cw)), fmaf(dir.z, ry, fmaf(o2.z, sw, o1.z * cw)) };
+}
+
+// computeOrthonormalBasisNaive, kernel.cu:76-84
+__device__ __forceinline__ void orthonormal_basis(const F3& w, F3& u, F3& v) {
+	const F3 a = ((double)fabsf(w.x) > .9) ? F3{ 0.0f, 1.0f, 0.0f } : F3{ 1.0f, 0.0f, 0.0f };
+	const F3 c{ fmaf(a.y, w.z, -(w.y * a.z)), fmaf(a.z, w.x, -(w.z * a.x)), fmaf(a.x, w.y, -(w.x * a.y)) };
+	u = normalize_ref(c);
+	v = F3{ fmaf(w.y, u.z, -(u.y * w.z)), fmaf(w.z, u.x, -(u.z * w.x)), fmaf(w.x, u.y, -(u.x * w.y)) };
+}
+
+// ---- path vertex state ----------------------------------------------------------------------------------------
+struct Ray {
+	F3 origin, direction, throughput, normal;
+	float distance;
+	int identifier, bounces;
+	uint32_t pixel_index;
+};
+
+// primary_rays body, kernel.cu:164-200. `index` counts NEW rays of this frame; pixel rows wrap inside the tile.
+__device__ __forceinline__ Ray generate_primary(const FrameParams& fp, uint32_t frame, uint32_t start_position, uint32_t index) {
+	uint32_t seed = (frame * 147565741u) * 720898027u * index;  // kernel.cu:165
+	const uint32_t rows = fp.tile_rows;
+	const uint32_t x = (start_position + index) % fp.width;                 // kernel.cu:170
+	const uint32_t ty = ((start_position + index) / fp.width) % rows;       // kernel.cu:171 (row inside the tile)
+	const uint32_t y = ty + fp.tile_row0;
+	float sx, sy;
+	stratified_sample(seed, sx, sy);
+	const float px = (float)x - sx;
+	const float py = (float)y - sy;
+	const float wf = (float)fp.width, hf = (float)fp.height;
+	const float ni = (px / wf) - 0.5f;
+	const float nj = ((hf - py) / hf) - 0.5f;
+	F3 d{ fmaf(nj, fp.cam_up.x, fmaf(ni, fp.cam_right.x, fp.cam_dir.x)), fmaf(nj, fp.cam_up.y, fmaf(ni, fp.cam_right.y, fp.cam_dir.y)),
+		  fmaf(nj, fp.cam_up.z, fmaf(ni, fp.cam_right.z, fp.cam_dir.z)) };
+	d = normalize_ref(d);
+	const F3 conv{ fmaf(fp.focal3, d.x, fp.cam_pos.x), fmaf(fp.focal3, d.y, fp.cam_pos.y), fmaf(fp.focal3, d.z, fp.cam_pos.z) };
+	const float l0 = random_float(seed);
+	const float l1 = random_float(seed);
+	float dx, dy;
+	concentric_disk(l0, l1, dx, dy);
+	const float plx = fp.lens_radius * dx, ply = fp.lens_radius * dy;
+	Ray r;
+	r.origin = F3{ fmaf(ply, fp.cam_up.x, fmaf(plx, fp.cam_right.x, fp.cam_pos.x)), fmaf(ply, fp.cam_up.y, fmaf(plx, fp.cam_right.y, fp.cam_pos.y)),
+		           fmaf(ply, fp.cam_up.z, fmaf(plx, fp.cam_right.z, fp.cam_pos.z)) };
+	r.direction = normalize_ref(F3{ conv.x - r.origin.x, conv.y - r.origin.y, conv.z - r.origin.z });
+	r.throughput = F3{ 1.f, 1.f, 1.f };
+	r.normal = F3{ 0.f, 0.f, 0.f };
+	r.distance = 0.f;
+	r.identifier = 0;
+	r.bounces = 0;
+	r.pixel_index = ty * fp.width + x;  // index into this context's (tile) accumulation buffer
+	return r;
+}
+
+struct ShadeResult {
+	bool has_shadow, survives, terminated;
+	F3 shadow_dir, shadow_color;
+	F3 radiance;  // added to rgb when terminated by a miss
+	bool add_radiance;
+};
+
+// shade body, kernel.cu:251-323. Updates `ray` in place to the bounced ray when it survives.
+__device__ __forceinline__ ShadeResult shade_vertex(const FrameParams& fp, uint32_t frame, uint32_t slot, Ray& ray) {
+	ShadeResult s;
+	s.has_shadow = s.survives = s.terminated = s.add_radiance = false;
+	uint32_t seed = (frame * ray.pixel_index * 147565741u) * 720898027u * slot;  // kernel.cu:252
+	if (ray.distance < kVeryFar) {
+		const F3 d = ray.direction, n = ray.normal;
+		F3 o = ray.origin;
+		o = F3{ fmaf(ray.distance, d.x, o.x), fmaf(ray.distance, d.y, o.y), fmaf(ray.distance, d.z, o.z) };  // kernel.cu:256
+		o = F3{ fmaf(n.x + n.x, kEpsilon, o.x), fmaf(n.y + n.y, kEpsilon, o.y), fmaf(n.z + n.z, kEpsilon, o.z) };  // kernel.cu:258
+		ray.origin = o;
+		// throughput *= color(1) (kernel.cu:261,271)
+		const F3 L = cone_sample(fp.sun_dir, fp.cone_extent, seed);  // kernel.cu:274
+		const float sun_light = fmaf(n.z, L.z, fmaf(n.x, L.x, n.y * L.y));
+		if (sun_light > 0.f) {  // kernel.cu:276-279
+			const F3 sc = sun_radiance(fp, L);
+			s.has_shadow = true;
+			s.shadow_dir = L;
+			s.shadow_color = F3{ ((ray.throughput.x * sc.x) * sun_light) * 1E-5f, ((ray.throughput.y * sc.y) * sun_light) * 1E-5f,
+				                 ((ray.throughput.z * sc.z) * sun_light) * 1E-5f };
+		}
+		if (ray.bounces < kMaxBounces) {  // kernel.cu:281-299
+			const float r1 = random_float(seed) * (2.f * kPi);
+			const float r2 = random_float(seed);
+			const float r2s = sqrtf(r2);
+			F3 u, v;
+			orthonormal_basis(n, u, v);
+			const float cs = cosf(r1), sn = sinf(r1);
+			const float z = sqrtf(1.0f - r2);
+			const F3 nd{ fmaf(z, n.x, fmaf(r2s, u.x * cs, r2s * (v.x * sn))), fmaf(z, n.y, fmaf(r2s, u.y * cs, r2s * (v.y * sn))),
+				         fmaf(z, n.z, fmaf(r2s, u.z * cs, r2s * (v.z * sn))) };
+			ray.direction = normalize_ref(nd);
+			ray.bounces++;
+			s.survives = true;
+		} else {
+			s.terminated = true;  // kernel.cu:301
+		}
+	} else {  // kernel.cu:316-322
+		const F3 c = ray.bounces == 0 ? sunsky_radiance(fp, ray.direction) : sky_radiance(fp, ray.direction);
+		s.radiance = F3{ ray.throughput.x * c.x, ray.throughput.y * c.y, ray.throughput.z * c.z };
+		s.add_radiance = true;
+		s.terminated = true;
+	}
+	return s;
+}
+
+// 64-byte ray records as four 128-bit transactions (RayQueue layout, variables.h:43-52)
+__device__ __forceinline__ Ray load_ray(const bm_ray* p) {
+	const float4* q = reinterpret_cast<const float4*>(p);
+	const float4 a = q[0], b = q[1], c = q[2], d = q[3];
+	Ray r;
+	r.origin = F3{ a.x, a.y, a.z };
+	r.direction = F3{ a.w, b.x, b.y };
+	r.throughput = F3{ b.z, b.w, c.x };
+	r.normal = F3{ c.y, c.z, c.w };
+	r.distance = d.x;
+	r.identifier = __float_as_int(d.y);
+	r.bounces = __float_as_int(d.z);
+	r.pixel_index = __float_as_uint(d.w);
+	return r;
+}
+__device__ __forceinline__ void store_ray(bm_ray* p, const Ray& r) {
+	float4* q = reinterpret_cast<float4*>(p);
+	q[0] = make_float4(r.origin.x, r.origin.y, r.origin.z, r.direction.x);
+	q[1] = make_float4(r.direction.y, r.direction.z, r.throughput.x, r.throughput.y);
+	q[2] = make_float4(r.throughput.z, r.normal.x, r.normal.y, r.normal.z);
+	q[3] = make_float4(r.distance, __int_as_float(r.identifier), __int_as_float(r.bounces), __uint_as_float(r.pixel_index));
+}
+
+}  // namespace bm

@@ -1,0 +1,869 @@
+// Kernels and C ABI of the B200 path tracer (include/brickmap_b200.h).
+//
+// Execution model (B200-first, not the reference's five atomically-fed wavefront kernels, kernel.cu:412-420):
+//   * ONE persistent kernel per frame (frame_kernel). A thread owns one of the frame's N segment slots from ray
+//     generation (or survivor fetch) through extend, shade and its shadow ray, with the path vertex in registers;
+//     the 64-byte RayQueue record is touched once on the way in (survivors only) and once on the way out
+//     (survivors only), as four 128-bit transactions. The reference moves ~310 B per slot through HBM/L2.
+//   * Slots are handed out in tiles of 256 by one atomic per tile (the reference: one same-address atomic per
+//     ray per kernel, kernel.cu:158,228,245,330). Survivors of a tile are compacted in slot order with
+//     __ballot_sync/__popc + a shared-memory warp scan and written tile-locally; a 1-block scan kernel turns the
+//     tile counts into the next frame's slot numbering, advances the pixel cursor and the frame counter on the
+//     device (set_wavefront_globals, kernel.cu:122-139) -- no host round trip between frames.
+//   * The emptiness bitmap of the cell grid (1 bit per 4x4x4 cells at reference dims = 32 KiB) lives in shared
+//     memory; the DDA performs the reference's exact float step sequence but only loads an index word where the
+//     bitmap says the block is not empty. Index words of a flat arena are addressed directly (no pointer-table
+//     dependent load, voxel.cuh:197-198).
+//   * Slot order == "the reference scheduled one thread at a time", so seeds (kernel.cu:165,252) and results
+//     are reproducible and comparable with the reference launched <<<1,1>>>.
+#include <cuda_runtime.h>
+
+#include <cmath>
+#include <cstdio>
+#include <cstring>
+#include <new>
+
+#include "bm_device.cuh"
+
+namespace bm {
+
+constexpr int kTile = 256;  // slots per tile == threads per block
+
+struct DeviceState {
+	uint32_t primary_ray_cnt;  // kernel.cu:106
+	uint32_t start_position;   // kernel.cu:109
+	uint32_t shadow_ray_cnt;   // kernel.cu:119 (of the last frame)
+	uint32_t frame;            // kernel.cu:369
+	uint32_t tile_ticket;      // replaces raynr_primary/extend/shade/connect (kernel.cu:111-117)
+	uint32_t done;             // bm_render target reached
+	uint32_t pad0, pad1;
+	unsigned long long frames, extend_rays, shadow_rays, terminations, unoccluded, cell_steps, index_reads, bricks, requests;
+	unsigned long long paths_since_reset, target_paths;
+};
+
+struct FrameIO {
+	DeviceState* st;
+	const bm_ray* in;           // survivors of the previous frame: dense [0,c) when in_prefix == nullptr, else tile-local
+	const uint32_t* in_prefix;  // exclusive prefix of the previous frame's tile counts (ntiles + 1 entries)
+	bm_ray* out;                // survivors of this frame, tile-local (tile t at out + t * kTile)
+	uint32_t* out_count;        // per tile
+	bm_ray* record;             // RECORD: the reference's work queue, post-extend record of every slot
+	bm_shadow* shadow_out;      // RECORD: shadow rays, tile-local
+	uint32_t* shadow_count;     // RECORD: per tile
+	float4* accum;              // blit_buffer (state.h:22)
+	uint32_t ntiles;
+};
+
+__device__ __forceinline__ void accum_add(float4* accum, uint32_t pixel, float r, float g, float b, float a) {
+	// one 128-bit reduction instead of the reference's 3-4 scalar float atomics (kernel.cu:319-322,341-343)
+	atomicAdd(accum + pixel, make_float4(r, g, b, a));
+}
+
+// exclusive rank of `flag` among the block's threads in thread order; *total = block count
+__device__ __forceinline__ uint32_t block_rank(bool flag, uint32_t* s_warp, uint32_t* total) {
+	const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+	const uint32_t ballot = __ballot_sync(0xFFFFFFFFu, flag);
+	const uint32_t within = __popc(ballot & ((1u << lane) - 1u));
+	if (lane == 0) s_warp[warp] = __popc(ballot);
+	__syncthreads();
+	uint32_t base = 0, sum = 0;
+#pragma unroll
+	for (int w = 0; w < kTile / 32; w++) {
+		const uint32_t v = s_warp[w];
+		if (w < (int)warp) base += v;
+		sum += v;
+	}
+	__syncthreads();
+	*total = sum;
+	return base + within;
+}
+
+__device__ __forceinline__ unsigned long long warp_sum(unsigned long long v) {
+#pragma unroll
+	for (int o = 16; o > 0; o >>= 1) v += __shfl_down_sync(0xFFFFFFFFu, v, o);
+	return v;
+}
+
+template <bool RECORD, bool COUNT>
+__global__ void __launch_bounds__(kTile) frame_kernel(const FrameParams fp, const SceneView sv, const FrameIO io) {
+	extern __shared__ uint32_t s_coarse[];
+	__shared__ uint32_t s_tile;
+	__shared__ uint32_t s_warp[kTile / 32];
+	__shared__ unsigned long long s_stats[8];
+
+	DeviceState* st = io.st;
+	if (st->done) return;
+	const uint32_t* coarse = nullptr;
+	if (sv.coarse) {
+		for (uint32_t i = threadIdx.x; i < sv.coarse_words; i += blockDim.x) s_coarse[i] = __ldg(sv.coarse + i);
+		coarse = s_coarse;
+	}
+	if (threadIdx.x < 8) s_stats[threadIdx.x] = 0;
+	__syncthreads();
+
+	const uint32_t c = st->primary_ray_cnt;
+	const uint32_t start = st->start_position;
+	const uint32_t frame = st->frame;
+	unsigned long long n_shadow = 0, n_term = 0, n_unocc = 0;
+	WorkCounters wc{ 0, 0, 0, 0 };
+
+	for (;;) {
+		if (threadIdx.x == 0) s_tile = atomicAdd(&st->tile_ticket, 1u);
+		__syncthreads();
+		const uint32_t tile = s_tile;
+		if (tile >= io.ntiles) break;
+		const uint32_t slot = tile * kTile + threadIdx.x;
+		const bool valid = slot < fp.n_slots;
+		Ray ray;
+		bool survives = false, has_shadow = false;
+		F3 shadow_dir{ 0, 0, 0 }, shadow_color{ 0, 0, 0 };
+		if (valid) {
+			if (slot < c) {
+				const bm_ray* src = io.in + slot;
+				if (io.in_prefix) {
+					// survivor `slot` of the previous frame lives in source tile t = max{ t : prefix[t] <= slot }
+					uint32_t lo = 0, hi = io.ntiles;
+					while (hi - lo > 1) {
+						const uint32_t mid = (lo + hi) >> 1;
+						if (__ldg(io.in_prefix + mid) <= slot) lo = mid; else hi = mid;
+					}
+					src = io.in + (size_t)lo * kTile + (slot - __ldg(io.in_prefix + lo));
+				}
+				ray = load_ray(src);
+			} else {
+				ray = generate_primary(fp, frame, start, slot - c);  // primary_rays, kernel.cu:154-223
+			}
+			// extend, kernel.cu:226-238
+			ray.distance = kVeryFar;
+			intersect_voxel<COUNT>(sv, coarse, ray.origin, ray.direction, ray.normal, ray.distance, fp.cam_cell, &wc);
+			if (RECORD) store_ray(io.record + slot, ray);
+			// shade, kernel.cu:242-325
+			const ShadeResult s = shade_vertex(fp, frame, slot, ray);
+			survives = s.survives;
+			has_shadow = s.has_shadow;
+			shadow_dir = s.shadow_dir;
+			shadow_color = s.shadow_color;
+			if (s.add_radiance) accum_add(io.accum, ray.pixel_index, s.radiance.x, s.radiance.y, s.radiance.z, 1.f);
+			else if (s.terminated) accum_add(io.accum, ray.pixel_index, 0.f, 0.f, 0.f, 1.f);
+			n_term += s.terminated;
+			// connect, kernel.cu:328-346
+			if (has_shadow) {
+				F3 y{ 0.f, 0.f, 0.f };
+				float t = 0.f;
+				n_shadow++;
+				if (!intersect_voxel<COUNT>(sv, coarse, ray.origin, shadow_dir, y, t, fp.cam_cell, &wc)) {
+					accum_add(io.accum, ray.pixel_index, shadow_color.x, shadow_color.y, shadow_color.z, 0.f);
+					n_unocc++;
+				}
+			}
+		}
+		// stable (slot-ordered) compaction of the survivors: the reference's atomicAdd(&primary_ray_cnt,1)
+		// (kernel.cu:298-299) with the schedule fixed to slot order
+		uint32_t total;
+		const uint32_t rank = block_rank(survives, s_warp, &total);
+		if (survives) store_ray(io.out + (size_t)tile * kTile + rank, ray);
+		if (threadIdx.x == 0) io.out_count[tile] = total;
+		if (RECORD) {
+			uint32_t stotal;
+			const uint32_t srank = block_rank(has_shadow, s_warp, &stotal);
+			if (has_shadow) {
+				bm_shadow* q = io.shadow_out + (size_t)tile * kTile + srank;  // kernel.cu:277-278
+				q->origin[0] = ray.origin.x; q->origin[1] = ray.origin.y; q->origin[2] = ray.origin.z;
+				q->direction[0] = shadow_dir.x; q->direction[1] = shadow_dir.y; q->direction[2] = shadow_dir.z;
+				q->color[0] = shadow_color.x; q->color[1] = shadow_color.y; q->color[2] = shadow_color.z;
+				q->pixel_index = ray.pixel_index;
+			}
+			if (threadIdx.x == 0) io.shadow_count[tile] = stotal;
+		}
+	}
+
+	// per-block statistics -> a handful of atomics per block
+	n_shadow = warp_sum(n_shadow);
+	n_term = warp_sum(n_term);
+	n_unocc = warp_sum(n_unocc);
+	if ((threadIdx.x & 31) == 0) {
+		atomicAdd(&s_stats[0], n_shadow);
+		atomicAdd(&s_stats[1], n_term);
+		atomicAdd(&s_stats[2], n_unocc);
+	}
+	if (COUNT) {
+		const unsigned long long a = warp_sum(wc.index_reads), b = warp_sum(wc.bricks), q = warp_sum(wc.requests), t = warp_sum(wc.steps);
+		if ((threadIdx.x & 31) == 0) {
+			atomicAdd(&s_stats[3], a);
+			atomicAdd(&s_stats[4], b);
+			atomicAdd(&s_stats[5], q);
+			atomicAdd(&s_stats[6], t);
+		}
+	}
+	__syncthreads();
+	if (threadIdx.x == 0) {
+		if (s_stats[0]) atomicAdd(&st->shadow_rays, s_stats[0]);
+		if (s_stats[1]) atomicAdd(&st->terminations, s_stats[1]);
+		if (s_stats[1]) atomicAdd(&st->paths_since_reset, s_stats[1]);
+		if (s_stats[2]) atomicAdd(&st->unoccluded, s_stats[2]);
+		if (COUNT) {
+			atomicAdd(&st->index_reads, s_stats[3]);
+			atomicAdd(&st->bricks, s_stats[4]);
+			atomicAdd(&st->requests, s_stats[5]);
+			atomicAdd(&st->cell_steps, s_stats[6]);
+		}
+	}
+}
+
+// set_wavefront_globals (kernel.cu:122-139) + exclusive scan of the tile counts. One block.
+// counts[ntiles] -> prefix[ntiles + 1]; optional second pair for the shadow queue (RECORD).
+__global__ void __launch_bounds__(1024) scan_kernel(DeviceState* st, const uint32_t* counts, uint32_t* prefix, const uint32_t* shadow_counts,
+                                                     uint32_t* shadow_prefix, uint32_t ntiles, uint32_t n_slots, uint32_t pixels) {
+	__shared__ uint32_t s_part[1024];
+	if (st->done) return;
+	const uint32_t per = (ntiles + blockDim.x - 1) / blockDim.x;
+	for (int pass = 0; pass < 2; pass++) {
+		const uint32_t* in = pass == 0 ? counts : shadow_counts;
+		uint32_t* out = pass == 0 ? prefix : shadow_prefix;
+		if (!in) continue;
+		const uint32_t b = min(ntiles, threadIdx.x * per), e = min(ntiles, b + per);
+		uint32_t sum = 0;
+		for (uint32_t i = b; i < e; i++) sum += in[i];
+		s_part[threadIdx.x] = sum;
+		__syncthreads();
+		for (uint32_t off = 1; off < blockDim.x; off <<= 1) {  // Hillis-Steele inclusive scan of the partials
+			const uint32_t v = threadIdx.x >= off ? s_part[threadIdx.x - off] : 0;
+			__syncthreads();
+			s_part[threadIdx.x] += v;
+			__syncthreads();
+		}
+		uint32_t run = s_part[threadIdx.x] - sum;
+		for (uint32_t i = b; i < e; i++) {
+			out[i] = run;
+			run += in[i];
+		}
+		const uint32_t total = s_part[blockDim.x - 1];
+		__syncthreads();
+		if (threadIdx.x == 0) {
+			out[ntiles] = total;
+			if (pass == 0) {
+				const uint32_t progress = n_slots - st->primary_ray_cnt;  // kernel.cu:125
+				st->start_position = (st->start_position + progress) % pixels;  // kernel.cu:130-131
+				st->primary_ray_cnt = total;  // survivors written by shade (kernel.cu:298)
+				st->frame += 1;               // kernel.cu:423
+				st->tile_ticket = 0;
+				st->frames += 1;
+				st->extend_rays += n_slots;
+				if (st->target_paths && st->paths_since_reset >= st->target_paths) st->done = 1;
+			} else {
+				st->shadow_ray_cnt = total;
+			}
+		}
+		__syncthreads();
+	}
+}
+
+// tile-local -> dense (the layout the reference's queues have): dst[prefix[t] + j] = src[t * kTile + j]
+template <typename T>
+__global__ void __launch_bounds__(kTile) export_kernel(const T* src, const uint32_t* prefix, T* dst, uint32_t ntiles) {
+	const uint32_t tile = blockIdx.x;
+	if (tile >= ntiles) return;
+	const uint32_t base = prefix[tile], n = prefix[tile + 1] - base;
+	if (threadIdx.x < n) dst[base + threadIdx.x] = src[(size_t)tile * kTile + threadIdx.x];
+}
+
+// upload, kernel.cu:141-151, with the count read on the device (the reference copies it to the host first,
+// kernel.cu:408-409)
+__global__ void upload_kernel(const SceneView sv, const bm_brick* bricks_queue, const uint32_t* indices_queue) {
+	const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+	const uint32_t count = min(*sv.load_queue_count, sv.queue_size);
+	if (i >= count) return;
+	const int px = sv.load_queue[3 * i], py = sv.load_queue[3 * i + 1], pz = sv.load_queue[3 * i + 2];
+	const int sc = (px >> 4) + (py >> 4) * sv.supergrid_xy + (pz >> 4) * sv.supergrid_xy * sv.supergrid_xy;
+	const int local = (px & 15) + (py & 15) * 16 + (pz & 15) * 256;
+	const uint32_t word = indices_queue[i];
+	const uint4* s = reinterpret_cast<const uint4*>(bricks_queue + i);
+	uint4* d = reinterpret_cast<uint4*>(sv.bricks[sc] + (word & BM_BRICK_INDEX_BITS));
+	d[0] = s[0]; d[1] = s[1]; d[2] = s[2]; d[3] = s[3];
+	sv.indices[sc][local] = word;
+}
+
+// emptiness bitmap: bit b set iff any index word of coarse block b is non-zero
+__global__ void coarse_build_kernel(const SceneView sv, uint32_t* coarse, uint32_t nblocks) {
+	const uint32_t b = blockIdx.x * blockDim.x + threadIdx.x;
+	const int side = 1 << sv.coarse_shift;
+	bool any = false;
+	if (b < nblocks) {
+		const int bx = b % sv.coarse_nx, by = (b / sv.coarse_nx) % (sv.coarse_nxy / sv.coarse_nx), bz = b / sv.coarse_nxy;
+		for (int z = 0; z < side && !any; z++)
+			for (int y = 0; y < side && !any; y++)
+				for (int x = 0; x < side; x++) {
+					const int px = bx * side + x, py = by * side + y, pz = bz * side + z;
+					if (px >= sv.cells || py >= sv.cells || pz >= sv.cells_height) continue;
+					const int sc = (px >> 4) + (py >> 4) * sv.supergrid_xy + (pz >> 4) * sv.supergrid_xy * sv.supergrid_xy;
+					const int local = (px & 15) + (py & 15) * 16 + (pz & 15) * 256;
+					if (sv.indices[sc][local]) { any = true; break; }
+				}
+	}
+	const uint32_t ballot = __ballot_sync(0xFFFFFFFFu, any);
+	if ((threadIdx.x & 31) == 0 && (b >> 5) < sv.coarse_words) coarse[b >> 5] = ballot;
+}
+
+// is indices[sc] == indices[0] + sc * 4096 for every superchunk?
+__global__ void flat_check_kernel(uint32_t* const* indices, uint32_t n, uint32_t* not_flat) {
+	const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+	if (i < n && indices[i] != indices[0] + (size_t)i * 4096) atomicExch(not_flat, 1u);
+}
+
+__global__ void trace_kernel(const SceneView sv, I3 cam, size_t n, const float* origins, const float* directions, float* normals, float* distances, uint8_t* hits) {
+	extern __shared__ uint32_t s_coarse[];
+	const uint32_t* coarse = nullptr;
+	if (sv.coarse) {
+		for (uint32_t i = threadIdx.x; i < sv.coarse_words; i += blockDim.x) s_coarse[i] = __ldg(sv.coarse + i);
+		coarse = s_coarse;
+	}
+	__syncthreads();
+	for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
+		F3 nrm{ normals[3 * i], normals[3 * i + 1], normals[3 * i + 2] };
+		float dist = distances[i];
+		WorkCounters wc{ 0, 0, 0, 0 };
+		const bool h = intersect_voxel<false>(sv, coarse, F3{ origins[3 * i], origins[3 * i + 1], origins[3 * i + 2] },
+		                                      F3{ directions[3 * i], directions[3 * i + 1], directions[3 * i + 2] }, nrm, dist, cam, &wc);
+		normals[3 * i] = nrm.x; normals[3 * i + 1] = nrm.y; normals[3 * i + 2] = nrm.z;
+		distances[i] = dist;
+		hits[i] = h ? 1 : 0;
+	}
+}
+
+__global__ void sky_kernel(const FrameParams fp, size_t n, const float* dirs, int mode, float* out) {
+	const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+	if (i >= n) return;
+	const F3 d{ dirs[3 * i], dirs[3 * i + 1], dirs[3 * i + 2] };
+	const F3 c = mode == 0 ? sun_radiance(fp, d) : (mode == 1 ? sky_radiance(fp, d) : sunsky_radiance(fp, d));
+	out[3 * i] = c.x; out[3 * i + 1] = c.y; out[3 * i + 2] = c.z;
+}
+
+// blit_onto_framebuffer, kernel.cu:348-364 (rgb / alpha, gamma 1/2.2, alpha = 1)
+__global__ void tonemap_kernel(const float4* accum, float4* out, size_t pixels) {
+	const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+	if (i >= pixels) return;
+	const float4 c = accum[i];
+	const float g = 1.f / 2.2f;
+	out[i] = make_float4(powf(c.x / c.w, g), powf(c.y / c.w, g), powf(c.z / c.w, g), powf(1.f, g));
+}
+
+}  // namespace bm
+
+// ================================================================================================================
+// host side
+// ================================================================================================================
+using namespace bm;
+
+static thread_local char g_error[256] = "";
+static int fail_cuda(cudaError_t e, const char* what, int line) {
+	snprintf(g_error, sizeof(g_error), "%s: %s (bm_kernels.cu:%d)", what, cudaGetErrorString(e), line);
+	return (int)e;
+}
+static int fail_api(int code, const char* what) {
+	snprintf(g_error, sizeof(g_error), "%s", what);
+	return code;
+}
+#define CK(x) do { cudaError_t e_ = (x); if (e_ != cudaSuccess) return fail_cuda(e_, #x, __LINE__); } while (0)
+
+struct bm_context {
+	bm_config cfg;
+	cudaStream_t stream = nullptr;
+	int sm_count = 0;
+	uint32_t ntiles = 0;
+	uint32_t tile_pixels = 0;
+	DeviceState* d_state = nullptr;
+	// private survivor buffers (tile-local layout), tile counts and prefixes, double-buffered
+	bm_ray* d_rays[2] = { nullptr, nullptr };
+	uint32_t* d_count[2] = { nullptr, nullptr };
+	uint32_t* d_prefix[2] = { nullptr, nullptr };
+	bm_shadow* d_shadow = nullptr;  // RECORD scratch
+	uint32_t* d_shadow_count = nullptr;
+	uint32_t* d_shadow_prefix = nullptr;
+	int cur = 0;                 // which private buffer holds the survivors of the last frame
+	bool private_valid = false;  // survivors of the last frame are in d_rays[cur] (tile-local)
+	// scene
+	bool bound = false;
+	bm_gpu_scene scene{};
+	SceneView sv{};
+	uint32_t* d_coarse = nullptr;
+	uint32_t* d_flag = nullptr;
+	// host statics of launch_kernels (kernel.cu:367-382)
+	bm_camera cam{};
+	bm_camera last_cam{};
+	bool have_last = false;
+	float sun_x = 0.05f, sun_y = 0.1f;  // variables.cpp:3
+	bool sun_changed = true;            // variables.cpp:4
+	FrameParams fp{};
+	uint64_t launches = 0;
+	int frame_blocks = 0;
+	size_t frame_smem = 0;
+};
+
+static inline F3 h_cross(const F3& a, const F3& b) { return F3{ a.y * b.z - b.y * a.z, a.z * b.x - b.z * a.x, a.x * b.y - b.x * a.y }; }
+static inline F3 h_normalize(const F3& v) {
+	const float r = 1.0f / sqrtf(v.x * v.x + v.y * v.y + v.z * v.z);
+	return F3{ v.x * r, v.y * r, v.z * r };
+}
+
+// Per-frame constants: camera basis (kernel.cu:384-385), sun direction (kernel.cu:393, sunsky.cu:28-30) and the
+// view-independent factors of the sky model (sunsky.cu:10-26,36-66) evaluated once in double precision.
+static void update_frame_params(bm_context* c) {
+	FrameParams& fp = c->fp;
+	const bm_camera& cam = c->cam;
+	const F3 dir{ cam.direction[0], cam.direction[1], cam.direction[2] }, up{ cam.up[0], cam.up[1], cam.up[2] };
+	const float aspect = (float)(size_t)c->cfg.screen_width / (size_t)c->cfg.screen_height;
+	const F3 rn = h_normalize(h_cross(dir, up));
+	fp.cam_right = F3{ rn.x * 1.5f * aspect, rn.y * 1.5f * aspect, rn.z * 1.5f * aspect };
+	const F3 un = h_normalize(h_cross(fp.cam_right, dir));
+	fp.cam_up = F3{ un.x * 1.5f, un.y * 1.5f, un.z * 1.5f };
+	fp.cam_dir = dir;
+	fp.cam_pos = F3{ cam.position[0], cam.position[1], cam.position[2] };
+	fp.focal3 = cam.focal_distance * 3.0f;
+	fp.lens_radius = cam.lens_radius;
+	fp.cam_cell = I3{ (int)(cam.position[0] / 8.f), (int)(cam.position[1] / 8.f), (int)(cam.position[2] / 8.f) };
+	fp.width = c->cfg.screen_width;
+	fp.height = c->cfg.screen_height;
+	fp.tile_row0 = c->cfg.tile_row0;
+	fp.tile_rows = c->cfg.tile_rows;
+	fp.n_slots = c->cfg.ray_queue_buffer_size;
+
+	const float px = (c->sun_x - 0.0f) * 6.28f, py = (c->sun_y - 0.5f) * 3.14f;
+	const F3 p{ cosf(px) * sinf(py), sinf(px) * sinf(py), cosf(py) };
+	fp.sun_dir = h_normalize(p);
+	fp.sun_angular_cos = cosf(1.5f * kPi / 180.f);  // sunSize (sunsky.cuh:25), kernel.cu:374
+	fp.cone_extent = 1.0f - fp.sun_angular_cos;
+	// SunIntensity(cosSunUp), sunsky.cu:24-26: cutoffAngle = pi/1.95, steepness 1.5, sunIntensity 1000
+	const float cos_sun_up = fp.sun_dir.z;
+	const float cutoff = kPi / 1.95f;
+	const double e = 1.0 - (double)expf(-((cutoff - acosf(cos_sun_up)) / 1.5f));
+	fp.sun_e = (float)(1000.0 * (e > 0.0 ? e : 0.0));
+	fp.rayleigh = F3{ 5.176821E-6f, 1.2785348E-5f, 2.8530756E-5f };
+	// totalMie(primaryWavelengths, K, turbidity=1) * mieCoefficient, sunsky.cu:14-18,44
+	const float cc = (float)((0.2 * 1.0) * 10E-18);
+	const float k = 0.434f * cc * kPi;
+	const float lambda[3] = { 680E-9f, 550E-9f, 450E-9f }, K[3] = { 0.686f, 0.678f, 0.666f };
+	float mie[3];
+	for (int i = 0; i < 3; i++) mie[i] = (k * powf((2.0f * kPi) / lambda[i], 2.0f) * K[i]) * 0.005f;
+	fp.mie = F3{ mie[0], mie[1], mie[2] };
+	fp.total = F3{ fp.rayleigh.x + mie[0], fp.rayleigh.y + mie[1], fp.rayleigh.z + mie[2] };
+	const float a = powf(1.0f - fp.sun_dir.z, 5.0f);
+	fp.mix_a = a < 0.f ? 0.f : (a > 1.f ? 1.f : a);
+	fp.rayleigh_k = (float)(3.0 / (16.0 * (double)kPi));
+	fp.hg_g = 0.80f;
+	fp.hg_k = (float)((1.0 / (4.0 * (double)kPi)) * (1.0 - (double)(0.80f * 0.80f)));
+}
+
+extern "C" {
+
+const char* bm_last_error_string(void) { return g_error; }
+
+void bm_default_config(bm_config* cfg) {
+	memset(cfg, 0, sizeof(*cfg));
+	cfg->device = 0;
+	cfg->grid_size = 4096;                     // variables.h:7
+	cfg->grid_height = 512;                    // variables.h:8
+	cfg->lod_distance_2x2x2 = 100000;          // variables.h:27
+	cfg->lod_distance_8x8x8 = 600000;          // variables.h:25
+	cfg->brick_load_queue_size = 1024;         // variables.h:35
+	cfg->ray_queue_buffer_size = 2 * 1048576;  // variables.h:61
+	cfg->screen_width = 1920;
+	cfg->screen_height = 1080;
+	cfg->tile_row0 = 0;
+	cfg->tile_rows = 0;
+}
+
+void bm_destroy(bm_context* c) {
+	if (!c) return;
+	cudaSetDevice(c->cfg.device);
+	for (int i = 0; i < 2; i++) {
+		cudaFree(c->d_rays[i]);
+		cudaFree(c->d_count[i]);
+		cudaFree(c->d_prefix[i]);
+	}
+	cudaFree(c->d_shadow);
+	cudaFree(c->d_shadow_count);
+	cudaFree(c->d_shadow_prefix);
+	cudaFree(c->d_state);
+	cudaFree(c->d_coarse);
+	cudaFree(c->d_flag);
+	if (c->stream) cudaStreamDestroy(c->stream);
+	delete c;
+}
+
+int bm_create(bm_context** out, const bm_config* cfg) {
+	if (!out || !cfg) return fail_api(BM_E_INVALID, "bm_create: null argument");
+	if (cfg->grid_size <= 0 || cfg->grid_height <= 0 || cfg->grid_size % 128 || cfg->grid_height % 128)
+		return fail_api(BM_E_INVALID, "bm_create: grid dimensions must be positive multiples of 128");
+	if (!cfg->screen_width || !cfg->screen_height || !cfg->ray_queue_buffer_size || cfg->brick_load_queue_size <= 0)
+		return fail_api(BM_E_INVALID, "bm_create: zero-sized image or queue");
+	if (cfg->tile_rows && cfg->tile_row0 + cfg->tile_rows > cfg->screen_height) return fail_api(BM_E_INVALID, "bm_create: tile exceeds the image");
+	bm_context* c = new (std::nothrow) bm_context();
+	if (!c) return fail_api(BM_E_NOMEM, "bm_create: out of host memory");
+	c->cfg = *cfg;
+	if (!c->cfg.tile_rows) {
+		c->cfg.tile_row0 = 0;
+		c->cfg.tile_rows = cfg->screen_height;
+	}
+	c->tile_pixels = c->cfg.tile_rows * c->cfg.screen_width;
+	const uint32_t n = c->cfg.ray_queue_buffer_size;
+	c->ntiles = (n + kTile - 1) / kTile;
+#define CKC(x) do { cudaError_t e_ = (x); if (e_ != cudaSuccess) { int rc_ = fail_cuda(e_, #x, __LINE__); bm_destroy(c); return rc_; } } while (0)
+	CKC(cudaSetDevice(cfg->device));
+	cudaDeviceProp props;
+	CKC(cudaGetDeviceProperties(&props, cfg->device));
+	c->sm_count = props.multiProcessorCount;
+	CKC(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
+	CKC(cudaMalloc(&c->d_state, sizeof(DeviceState)));
+	CKC(cudaMemset(c->d_state, 0, sizeof(DeviceState)));
+	const uint32_t one = 1;
+	CKC(cudaMemcpy(&c->d_state->frame, &one, 4, cudaMemcpyHostToDevice));
+	for (int i = 0; i < 2; i++) {
+		CKC(cudaMalloc(&c->d_rays[i], (size_t)c->ntiles * kTile * sizeof(bm_ray)));
+		CKC(cudaMalloc(&c->d_count[i], (size_t)c->ntiles * 4));
+		CKC(cudaMalloc(&c->d_prefix[i], (size_t)(c->ntiles + 1) * 4));
+		CKC(cudaMemset(c->d_count[i], 0, (size_t)c->ntiles * 4));
+		CKC(cudaMemset(c->d_prefix[i], 0, (size_t)(c->ntiles + 1) * 4));
+	}
+	CKC(cudaMalloc(&c->d_shadow_count, (size_t)c->ntiles * 4));
+	CKC(cudaMalloc(&c->d_shadow_prefix, (size_t)(c->ntiles + 1) * 4));
+	CKC(cudaMalloc(&c->d_flag, 4));
+#undef CKC
+	// default camera (camera.h:4-9) and sun (variables.cpp:3)
+	const bm_camera def = { { 512, 512, 300 }, { 1, 0, 0 }, { 0, 0, 1 }, 1.f, 0.f };
+	c->cam = def;
+	update_frame_params(c);
+	*out = c;
+	return 0;
+}
+
+int bm_scene_bind(bm_context* c, bm_gpu_scene scene) {
+	if (!c) return fail_api(BM_E_INVALID, "bm_scene_bind: null context");
+	if (!scene.indices || !scene.bricks || !scene.brick_load_queue || !scene.brick_load_queue_count)
+		return fail_api(BM_E_INVALID, "bm_scene_bind: null scene pointer");
+	CK(cudaSetDevice(c->cfg.device));
+	c->scene = scene;
+	SceneView& sv = c->sv;
+	sv.indices = scene.indices;
+	sv.bricks = scene.bricks;
+	sv.load_queue = scene.brick_load_queue;
+	sv.load_queue_count = scene.brick_load_queue_count;
+	sv.cells = c->cfg.grid_size / 8;
+	sv.cells_height = c->cfg.grid_height / 8;
+	sv.supergrid_xy = sv.cells / 16;
+	sv.grid_size_f = (float)c->cfg.grid_size;
+	sv.grid_height_f = (float)c->cfg.grid_height;
+	sv.lod2 = c->cfg.lod_distance_2x2x2;
+	sv.lod8 = c->cfg.lod_distance_8x8x8;
+	sv.queue_size = (uint32_t)c->cfg.brick_load_queue_size;
+	// emptiness bitmap: the finest block size whose bitmap fits in 64 KiB of shared memory
+	int shift = 0;
+	uint64_t bits;
+	for (;; shift++) {
+		const uint64_t nx = (uint64_t)(sv.cells + (1 << shift) - 1) >> shift, nz = (uint64_t)(sv.cells_height + (1 << shift) - 1) >> shift;
+		bits = nx * nx * nz;
+		if (bits <= 64u * 1024u * 8u) break;
+	}
+	sv.coarse_shift = shift;
+	sv.coarse_nx = (sv.cells + (1 << shift) - 1) >> shift;
+	sv.coarse_nxy = sv.coarse_nx * sv.coarse_nx;
+	sv.coarse_words = (uint32_t)((bits + 31) / 32);
+	cudaFree(c->d_coarse);
+	c->d_coarse = nullptr;
+	CK(cudaMalloc(&c->d_coarse, (size_t)(sv.coarse_words + 1) * 4));
+	CK(cudaMemsetAsync(c->d_coarse, 0, (size_t)(sv.coarse_words + 1) * 4, c->stream));
+	sv.coarse = nullptr;
+	sv.flat_indices = nullptr;
+	const uint32_t nblocks = (uint32_t)bits;
+	coarse_build_kernel<<<(sv.coarse_words * 32 + 255) / 256, 256, 0, c->stream>>>(sv, c->d_coarse, nblocks);
+	CK(cudaGetLastError());
+	const uint32_t nsc = (uint32_t)(sv.supergrid_xy * sv.supergrid_xy * (sv.cells_height / 16));
+	CK(cudaMemsetAsync(c->d_flag, 0, 4, c->stream));
+	flat_check_kernel<<<(nsc + 255) / 256, 256, 0, c->stream>>>(scene.indices, nsc, c->d_flag);
+	CK(cudaGetLastError());
+	c->launches += 2;
+	uint32_t not_flat = 1;
+	uint32_t* first = nullptr;
+	CK(cudaMemcpyAsync(&not_flat, c->d_flag, 4, cudaMemcpyDeviceToHost, c->stream));
+	CK(cudaMemcpyAsync(&first, scene.indices, sizeof(uint32_t*), cudaMemcpyDeviceToHost, c->stream));
+	CK(cudaStreamSynchronize(c->stream));
+	sv.coarse = c->d_coarse;
+	sv.flat_indices = not_flat ? nullptr : first;
+	// launch geometry of the persistent frame kernel
+	c->frame_smem = (size_t)sv.coarse_words * 4;
+	CK(cudaFuncSetAttribute(frame_kernel<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)c->frame_smem));
+	CK(cudaFuncSetAttribute(frame_kernel<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)c->frame_smem));
+	CK(cudaFuncSetAttribute(frame_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)c->frame_smem));
+	CK(cudaFuncSetAttribute(frame_kernel<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)c->frame_smem));
+	CK(cudaFuncSetAttribute(trace_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)c->frame_smem));
+	int per_sm = 0;
+	CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, frame_kernel<false, false>, kTile, c->frame_smem));
+	if (per_sm < 1) per_sm = 1;
+	c->frame_blocks = c->sm_count * per_sm;
+	c->bound = true;
+	return 0;
+}
+
+int bm_set_camera(bm_context* c, const bm_camera* cam) {
+	if (!c || !cam) return fail_api(BM_E_INVALID, "bm_set_camera: null argument");
+	c->cam = *cam;
+	update_frame_params(c);
+	return 0;
+}
+
+int bm_set_sun(bm_context* c, float x, float y) {
+	if (!c) return fail_api(BM_E_INVALID, "bm_set_sun: null context");
+	c->sun_x = x;
+	c->sun_y = y;
+	c->sun_changed = true;  // kernel.cu:389
+	update_frame_params(c);
+	return 0;
+}
+
+int bm_get_counters(bm_context* c, bm_counters* out) {
+	if (!c || !out) return fail_api(BM_E_INVALID, "bm_get_counters: null argument");
+	CK(cudaSetDevice(c->cfg.device));
+	CK(cudaStreamSynchronize(c->stream));
+	DeviceState s;
+	CK(cudaMemcpy(&s, c->d_state, sizeof(s), cudaMemcpyDeviceToHost));
+	out->primary_ray_cnt = s.primary_ray_cnt;
+	out->start_position = s.start_position;
+	out->shadow_ray_cnt = s.shadow_ray_cnt;
+	out->frame = s.frame;
+	return 0;
+}
+
+int bm_set_counters(bm_context* c, const bm_counters* in) {
+	if (!c || !in) return fail_api(BM_E_INVALID, "bm_set_counters: null argument");
+	CK(cudaSetDevice(c->cfg.device));
+	CK(cudaStreamSynchronize(c->stream));
+	const uint32_t v[4] = { in->primary_ray_cnt, in->start_position, in->shadow_ray_cnt, in->frame };
+	CK(cudaMemcpy(c->d_state, v, sizeof(v), cudaMemcpyHostToDevice));
+	c->private_valid = false;  // the caller now owns the meaning of the survivor set (dense `queue`)
+	return 0;
+}
+
+int bm_get_stats(bm_context* c, bm_stats* out) {
+	if (!c || !out) return fail_api(BM_E_INVALID, "bm_get_stats: null argument");
+	CK(cudaSetDevice(c->cfg.device));
+	CK(cudaStreamSynchronize(c->stream));
+	DeviceState s;
+	CK(cudaMemcpy(&s, c->d_state, sizeof(s), cudaMemcpyDeviceToHost));
+	out->frames = s.frames;
+	out->extend_rays = s.extend_rays;
+	out->shadow_rays = s.shadow_rays;
+	out->terminations = s.terminations;
+	out->unoccluded = s.unoccluded;
+	out->cell_steps = s.cell_steps;
+	out->index_reads = s.index_reads;
+	out->bricks_entered = s.bricks;
+	out->requests = s.requests;
+	out->kernel_launches = c->launches;
+	return 0;
+}
+
+int bm_reset_stats(bm_context* c) {
+	if (!c) return fail_api(BM_E_INVALID, "bm_reset_stats: null context");
+	CK(cudaSetDevice(c->cfg.device));
+	CK(cudaStreamSynchronize(c->stream));
+	CK(cudaMemset(&c->d_state->frames, 0, 9 * sizeof(unsigned long long)));
+	c->launches = 0;
+	return 0;
+}
+
+void* bm_stream(bm_context* c) { return c ? (void*)c->stream : nullptr; }
+
+int bm_synchronize(bm_context* c) {
+	if (!c) return fail_api(BM_E_INVALID, "bm_synchronize: null context");
+	CK(cudaStreamSynchronize(c->stream));
+	return 0;
+}
+
+}  // extern "C"
+
+// reset logic of launch_kernels (kernel.cu:387-403): camera / lens / sun change -> zero the accumulation buffer and
+// primary_ray_cnt (NOT start_position, NOT frame)
+static int maybe_reset(bm_context* c, float* blit, uint32_t flags) {
+	bool reset = !c->have_last || memcmp(c->last_cam.position, c->cam.position, 12) != 0 || memcmp(c->last_cam.direction, c->cam.direction, 12) != 0 ||
+	             c->last_cam.focal_distance != c->cam.focal_distance || c->last_cam.lens_radius != c->cam.lens_radius;
+	if (!c->have_last) {
+		// first call: last_pos/last_dir are zero-initialised statics, last_focaldistance = 1, last_lensradius = 0.02f
+		// (kernel.cu:379-382) -> the comparison is true for any usable camera
+		reset = true;
+	}
+	if (c->sun_changed) {
+		c->sun_changed = false;
+		reset = true;
+	}
+	c->last_cam = c->cam;
+	c->have_last = true;
+	if (reset && !(flags & BM_FRAME_NO_RESET)) {
+		CK(cudaMemsetAsync(blit, 0, (size_t)c->tile_pixels * 16, c->stream));
+		CK(cudaMemsetAsync(&c->d_state->primary_ray_cnt, 0, 4, c->stream));
+		CK(cudaMemsetAsync(&c->d_state->paths_since_reset, 0, 8, c->stream));
+		CK(cudaMemsetAsync(&c->d_state->done, 0, 4, c->stream));
+	}
+	return 0;
+}
+
+static int launch_upload(bm_context* c) {
+	const uint32_t q = c->sv.queue_size;
+	upload_kernel<<<(q + 255) / 256, 256, 0, c->stream>>>(c->sv, c->scene.bricks_queue, c->scene.indices_queue);
+	CK(cudaGetLastError());
+	CK(cudaMemsetAsync(c->scene.brick_load_queue_count, 0, 4, c->stream));  // kernel.cu:413
+	c->launches += 1;
+	return 0;
+}
+
+template <bool RECORD>
+static int launch_frame_kernels(bm_context* c, const FrameIO& io, bool count) {
+	const int blocks = (int)(c->ntiles < (uint32_t)c->frame_blocks ? c->ntiles : (uint32_t)c->frame_blocks);
+	if (count) frame_kernel<RECORD, true><<<blocks, kTile, c->frame_smem, c->stream>>>(c->fp, c->sv, io);
+	else frame_kernel<RECORD, false><<<blocks, kTile, c->frame_smem, c->stream>>>(c->fp, c->sv, io);
+	CK(cudaGetLastError());
+	scan_kernel<<<1, 1024, 0, c->stream>>>(c->d_state, io.out_count, c->d_prefix[c->cur ^ 1], RECORD ? io.shadow_count : nullptr,
+	                                       RECORD ? c->d_shadow_prefix : nullptr, c->ntiles, c->cfg.ray_queue_buffer_size, c->tile_pixels);
+	CK(cudaGetLastError());
+	c->launches += 2;
+	return 0;
+}
+
+extern "C" {
+
+int bm_launch_frame(bm_context* c, float* blit, bm_ray* queue, bm_ray* queue2, bm_shadow* shadow_queue, uint32_t flags) {
+	if (!c || !blit || !queue || !queue2 || !shadow_queue) return fail_api(BM_E_INVALID, "bm_launch_frame: null argument");
+	if (!c->bound) return fail_api(BM_E_STATE, "bm_launch_frame: no scene bound (bm_scene_bind)");
+	CK(cudaSetDevice(c->cfg.device));
+	if (!c->d_shadow) CK(cudaMalloc(&c->d_shadow, (size_t)c->ntiles * kTile * sizeof(bm_shadow)));
+	int rc = maybe_reset(c, blit, flags);
+	if (rc) return rc;
+	if (!(flags & BM_FRAME_NO_UPLOAD) && c->scene.bricks_queue && c->scene.indices_queue) {
+		rc = launch_upload(c);
+		if (rc) return rc;
+	}
+	CK(cudaMemsetAsync(&c->d_state->done, 0, 4, c->stream));
+	CK(cudaMemsetAsync(&c->d_state->target_paths, 0, 8, c->stream));
+	FrameIO io{};
+	io.st = c->d_state;
+	if (c->private_valid) {
+		// survivors of the previous frame are still in the private tile-local buffer; the caller's swapped `queue`
+		// holds the same records densely (main.cpp:146) and is not needed
+		io.in = c->d_rays[c->cur];
+		io.in_prefix = c->d_prefix[c->cur];
+	} else {
+		io.in = queue;  // dense survivors [0, primary_ray_cnt) supplied by the caller (after bm_set_counters)
+		io.in_prefix = nullptr;
+	}
+	io.out = c->d_rays[c->cur ^ 1];
+	io.out_count = c->d_count[c->cur ^ 1];
+	io.record = queue;
+	io.shadow_out = c->d_shadow;
+	io.shadow_count = c->d_shadow_count;
+	io.accum = reinterpret_cast<float4*>(blit);
+	io.ntiles = c->ntiles;
+	rc = launch_frame_kernels<true>(c, io, (flags & BM_FRAME_COUNT_WORK) != 0);
+	if (rc) return rc;
+	c->cur ^= 1;
+	export_kernel<bm_ray><<<c->ntiles, kTile, 0, c->stream>>>(c->d_rays[c->cur], c->d_prefix[c->cur], queue2, c->ntiles);
+	CK(cudaGetLastError());
+	export_kernel<bm_shadow><<<c->ntiles, kTile, 0, c->stream>>>(c->d_shadow, c->d_shadow_prefix, shadow_queue, c->ntiles);
+	CK(cudaGetLastError());
+	c->launches += 2;
+	c->private_valid = true;
+	CK(cudaStreamSynchronize(c->stream));  // kernel.cu:431
+	return 0;
+}
+
+int bm_render(bm_context* c, float* blit, uint32_t frames, uint64_t target_paths, uint32_t flags, int sync) {
+	if (!c || !blit) return fail_api(BM_E_INVALID, "bm_render: null argument");
+	if (!c->bound) return fail_api(BM_E_STATE, "bm_render: no scene bound (bm_scene_bind)");
+	CK(cudaSetDevice(c->cfg.device));
+	int rc = maybe_reset(c, blit, flags);
+	if (rc) return rc;
+	CK(cudaMemsetAsync(&c->d_state->done, 0, 4, c->stream));
+	const unsigned long long tp = target_paths;
+	CK(cudaMemcpyAsync(&c->d_state->target_paths, &tp, 8, cudaMemcpyHostToDevice, c->stream));
+	if (!c->private_valid) {
+		// no private survivor set (first frame, or the counters were set by the caller): start from an empty one
+		CK(cudaMemsetAsync(&c->d_state->primary_ray_cnt, 0, 4, c->stream));
+		CK(cudaMemsetAsync(c->d_prefix[c->cur], 0, (size_t)(c->ntiles + 1) * 4, c->stream));
+		c->private_valid = true;
+	}
+	for (uint32_t f = 0; f < frames; f++) {
+		if (!(flags & BM_FRAME_NO_UPLOAD) && c->scene.bricks_queue && c->scene.indices_queue) {
+			rc = launch_upload(c);
+			if (rc) return rc;
+		}
+		FrameIO io{};
+		io.st = c->d_state;
+		io.in = c->d_rays[c->cur];
+		io.in_prefix = c->d_prefix[c->cur];
+		io.out = c->d_rays[c->cur ^ 1];
+		io.out_count = c->d_count[c->cur ^ 1];
+		io.accum = reinterpret_cast<float4*>(blit);
+		io.ntiles = c->ntiles;
+		rc = launch_frame_kernels<false>(c, io, (flags & BM_FRAME_COUNT_WORK) != 0);
+		if (rc) return rc;
+		c->cur ^= 1;
+	}
+	if (sync) CK(cudaStreamSynchronize(c->stream));
+	return 0;
+}
+
+int bm_render_to_host(bm_context* c, float* blit, uint32_t frames, uint64_t target_paths, uint32_t flags, float* accum_host, uint32_t* request_count_host,
+                      int32_t* request_positions_host) {
+	int rc = bm_render(c, blit, frames, target_paths, flags, 0);
+	if (rc) return rc;
+	if (accum_host) CK(cudaMemcpyAsync(accum_host, blit, (size_t)c->tile_pixels * 16, cudaMemcpyDeviceToHost, c->stream));
+	if (request_count_host) CK(cudaMemcpyAsync(request_count_host, c->scene.brick_load_queue_count, 4, cudaMemcpyDeviceToHost, c->stream));
+	if (request_positions_host)
+		CK(cudaMemcpyAsync(request_positions_host, c->scene.brick_load_queue, (size_t)c->sv.queue_size * 12, cudaMemcpyDeviceToHost, c->stream));
+	CK(cudaStreamSynchronize(c->stream));
+	return 0;
+}
+
+int bm_read_requests(bm_context* c, uint32_t* count_host, int32_t* positions_host) {
+	if (!c) return fail_api(BM_E_INVALID, "bm_read_requests: null context");
+	if (!c->bound) return fail_api(BM_E_STATE, "bm_read_requests: no scene bound (bm_scene_bind)");
+	CK(cudaSetDevice(c->cfg.device));
+	if (count_host) CK(cudaMemcpyAsync(count_host, c->scene.brick_load_queue_count, 4, cudaMemcpyDeviceToHost, c->stream));
+	if (positions_host) CK(cudaMemcpyAsync(positions_host, c->scene.brick_load_queue, (size_t)c->sv.queue_size * 12, cudaMemcpyDeviceToHost, c->stream));
+	CK(cudaStreamSynchronize(c->stream));
+	return 0;
+}
+
+int bm_trace(bm_context* c, size_t n, const float* origins, const float* directions, float* normals, float* distances, uint8_t* hits) {
+	if (!c || (n && (!origins || !directions || !normals || !distances || !hits))) return fail_api(BM_E_INVALID, "bm_trace: null argument");
+	if (!c->bound) return fail_api(BM_E_STATE, "bm_trace: no scene bound (bm_scene_bind)");
+	if (!n) return 0;
+	CK(cudaSetDevice(c->cfg.device));
+	size_t blocks = (n + kTile - 1) / kTile;
+	if (blocks > (size_t)c->frame_blocks) blocks = (size_t)c->frame_blocks;
+	trace_kernel<<<(unsigned)blocks, kTile, c->frame_smem, c->stream>>>(c->sv, c->fp.cam_cell, n, origins, directions, normals, distances, hits);
+	CK(cudaGetLastError());
+	c->launches += 1;
+	CK(cudaStreamSynchronize(c->stream));
+	return 0;
+}
+
+int bm_eval_sky(bm_context* c, size_t n, const float* dirs, int mode, float* out) {
+	if (!c || mode < 0 || mode > 2 || (n && (!dirs || !out))) return fail_api(BM_E_INVALID, "bm_eval_sky: bad argument");
+	if (!n) return 0;
+	CK(cudaSetDevice(c->cfg.device));
+	sky_kernel<<<(unsigned)((n + 255) / 256), 256, 0, c->stream>>>(c->fp, n, dirs, mode, out);
+	CK(cudaGetLastError());
+	c->launches += 1;
+	CK(cudaStreamSynchronize(c->stream));
+	return 0;
+}
+
+int bm_tonemap(bm_context* c, const float* blit, float* out) {
+	if (!c || !blit || !out) return fail_api(BM_E_INVALID, "bm_tonemap: null argument");
+	CK(cudaSetDevice(c->cfg.device));
+	tonemap_kernel<<<(c->tile_pixels + 255) / 256, 256, 0, c->stream>>>(reinterpret_cast<const float4*>(blit), reinterpret_cast<float4*>(out), c->tile_pixels);
+	CK(cudaGetLastError());
+	c->launches += 1;
+	CK(cudaStreamSynchronize(c->stream));
+	return 0;
+}
+
+}  // extern "C"
