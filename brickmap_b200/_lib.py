@@ -52,6 +52,10 @@ SIGNATURES = {
     "bm_launch_frame": (C.c_int, [_P, _P, _P, _P, _P, C.c_uint32]),
     "bm_render": (C.c_int, [_P, _P, C.c_uint32, C.c_uint64, C.c_uint32, C.c_int]),
     "bm_render_to_host": (C.c_int, [_P, _P, C.c_uint32, C.c_uint64, C.c_uint32, _P, _P, _P]),
+    "bm_requests_pack": (C.c_int, [_P, _P]),
+    "bm_requests_merge": (C.c_int, [_P, _P, C.c_int]),
+    "bm_kernel_timing": (C.c_int, [_P, C.c_int]),
+    "bm_kernel_time": (C.c_int, [_P, C.POINTER(C.c_double), C.POINTER(C.c_uint64)]),
     "bm_read_requests": (C.c_int, [_P, _P, _P]),
     "bm_stream": (_P, [_P]),
     "bm_synchronize": (C.c_int, [_P]),

@@ -22,6 +22,7 @@
 #include <cstdio>
 #include <cstring>
 #include <new>
+#include <vector>
 
 #include "bm_device.cuh"
 
@@ -258,6 +259,13 @@ __global__ void __launch_bounds__(1024) scan_kernel(DeviceState* st, const uint3
 	}
 }
 
+// start of a bm_render / bm_launch_frame call: install the stop target; a target that is already met stops at once
+__global__ void begin_kernel(DeviceState* st, unsigned long long target_paths) {
+	st->target_paths = target_paths;
+	st->done = (target_paths && st->paths_since_reset >= target_paths) ? 1u : 0u;
+	st->tile_ticket = 0;
+}
+
 // tile-local -> dense (the layout the reference's queues have): dst[prefix[t] + j] = src[t * kTile + j]
 template <typename T>
 __global__ void __launch_bounds__(kTile) export_kernel(const T* src, const uint32_t* prefix, T* dst, uint32_t ntiles) {
@@ -281,6 +289,79 @@ __global__ void upload_kernel(const SceneView sv, const bm_brick* bricks_queue, 
 	uint4* d = reinterpret_cast<uint4*>(sv.bricks[sc] + (word & BM_BRICK_INDEX_BITS));
 	d[0] = s[0]; d[1] = s[1]; d[2] = s[2]; d[3] = s[3];
 	sv.indices[sc][local] = word;
+}
+
+// Merge of the all-gathered request blocks (see include/brickmap_b200.h). One block of 1024 threads.
+// gathered: world blocks of (1 + 3q) int32 = {count, positions}. Entry order: rank-major, queue order inside.
+__global__ void __launch_bounds__(1024) requests_merge_kernel(const SceneView sv, const int32_t* gathered, int world) {
+	extern __shared__ int32_t s_mem[];
+	const uint32_t q = sv.queue_size;
+	const uint32_t stride = 1 + 3 * q;
+	int32_t* s_key_x = s_mem;                      // world * q
+	int32_t* s_key_y = s_key_x + (size_t)world * q;
+	int32_t* s_key_z = s_key_y + (size_t)world * q;
+	int32_t* s_flag = s_key_z + (size_t)world * q;  // 1 = first occurrence
+	__shared__ uint32_t s_total;
+	__shared__ uint32_t s_base[32];
+	// flatten
+	uint32_t n = 0;
+	for (int r = 0; r < world; r++) n += min((uint32_t)gathered[(size_t)r * stride], q);
+	for (uint32_t i = threadIdx.x; i < n; i += blockDim.x) {
+		uint32_t k = i;
+		int r = 0;
+		for (; r < world; r++) {
+			const uint32_t c = min((uint32_t)gathered[(size_t)r * stride], q);
+			if (k < c) break;
+			k -= c;
+		}
+		const int32_t* p = gathered + (size_t)r * stride + 1 + 3 * k;
+		s_key_x[i] = p[0]; s_key_y[i] = p[1]; s_key_z[i] = p[2];
+	}
+	__syncthreads();
+	for (uint32_t i = threadIdx.x; i < n; i += blockDim.x) {
+		int first = 1;
+		const int32_t x = s_key_x[i], y = s_key_y[i], z = s_key_z[i];
+		for (uint32_t j = 0; j < i; j++)
+			if (s_key_x[j] == x && s_key_y[j] == y && s_key_z[j] == z) { first = 0; break; }
+		s_flag[i] = first;
+	}
+	__syncthreads();
+	// ordered compaction: thread t handles the contiguous chunk [t*per, (t+1)*per)
+	const uint32_t per = (n + blockDim.x - 1) / blockDim.x;
+	const uint32_t b = min(n, threadIdx.x * per), e = min(n, b + per);
+	uint32_t mine = 0;
+	for (uint32_t i = b; i < e; i++) mine += s_flag[i];
+	uint32_t incl = mine;
+	const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+	for (int o = 1; o < 32; o <<= 1) {
+		const uint32_t v = __shfl_up_sync(0xFFFFFFFFu, incl, o);
+		if (lane >= (uint32_t)o) incl += v;
+	}
+	if (lane == 31) s_base[warp] = incl;
+	__syncthreads();
+	if (threadIdx.x == 0) {
+		uint32_t run = 0;
+		for (int w = 0; w < 32; w++) { const uint32_t v = s_base[w]; s_base[w] = run; run += v; }
+		s_total = run;
+	}
+	__syncthreads();
+	uint32_t out = s_base[warp] + incl - mine;
+	for (uint32_t i = b; i < e; i++) {
+		if (!s_flag[i]) continue;
+		const int px = s_key_x[i], py = s_key_y[i], pz = s_key_z[i];
+		const int sc = (px >> 4) + (py >> 4) * sv.supergrid_xy + (pz >> 4) * sv.supergrid_xy * sv.supergrid_xy;
+		const int local = (px & 15) + (py & 15) * 16 + (pz & 15) * 256;
+		uint32_t* word = sv.indices[sc] + local;
+		if (out < q) {
+			sv.load_queue[3 * out] = px; sv.load_queue[3 * out + 1] = py; sv.load_queue[3 * out + 2] = pz;
+			atomicOr(word, BM_BRICK_REQUESTED_BIT);
+		} else {
+			atomicAnd(word, ~BM_BRICK_REQUESTED_BIT);
+		}
+		out++;
+	}
+	__syncthreads();
+	if (threadIdx.x == 0) *sv.load_queue_count = s_total;  // may exceed q, consumers clamp (kernel.cu:409)
 }
 
 // emptiness bitmap: bit b set iff any index word of coarse block b is non-zero
@@ -395,6 +476,12 @@ struct bm_context {
 	bool sun_changed = true;            // variables.cpp:4
 	FrameParams fp{};
 	uint64_t launches = 0;
+	// optional per-launch timing of frame_kernel
+	bool timing = false;
+	std::vector<cudaEvent_t> events;  // pairs
+	size_t events_used = 0;
+	double timed_ms = 0;
+	uint64_t timed_launches = 0;
 	int frame_blocks = 0;
 	size_t frame_smem = 0;
 };
@@ -486,6 +573,7 @@ void bm_destroy(bm_context* c) {
 	cudaFree(c->d_state);
 	cudaFree(c->d_coarse);
 	cudaFree(c->d_flag);
+	for (cudaEvent_t e : c->events) cudaEventDestroy(e);
 	if (c->stream) cudaStreamDestroy(c->stream);
 	delete c;
 }
@@ -714,12 +802,43 @@ static int launch_upload(bm_context* c) {
 	return 0;
 }
 
+static int drain_events(bm_context* c) {
+	if (c->events_used) {
+		CK(cudaEventSynchronize(c->events[c->events_used - 1]));
+		for (size_t i = 0; i + 1 < c->events_used; i += 2) {
+			float ms = 0.f;
+			CK(cudaEventElapsedTime(&ms, c->events[i], c->events[i + 1]));
+			c->timed_ms += ms;
+			c->timed_launches += 1;
+		}
+		c->events_used = 0;
+	}
+	return 0;
+}
+
 template <bool RECORD>
 static int launch_frame_kernels(bm_context* c, const FrameIO& io, bool count) {
 	const int blocks = (int)(c->ntiles < (uint32_t)c->frame_blocks ? c->ntiles : (uint32_t)c->frame_blocks);
+	cudaEvent_t e0 = nullptr, e1 = nullptr;
+	if (c->timing) {
+		if (c->events_used + 2 > 8192) {
+			const int rc = drain_events(c);
+			if (rc) return rc;
+		}
+		while (c->events.size() < c->events_used + 2) {
+			cudaEvent_t e;
+			CK(cudaEventCreate(&e));
+			c->events.push_back(e);
+		}
+		e0 = c->events[c->events_used];
+		e1 = c->events[c->events_used + 1];
+		c->events_used += 2;
+		CK(cudaEventRecord(e0, c->stream));
+	}
 	if (count) frame_kernel<RECORD, true><<<blocks, kTile, c->frame_smem, c->stream>>>(c->fp, c->sv, io);
 	else frame_kernel<RECORD, false><<<blocks, kTile, c->frame_smem, c->stream>>>(c->fp, c->sv, io);
 	CK(cudaGetLastError());
+	if (c->timing) CK(cudaEventRecord(e1, c->stream));
 	scan_kernel<<<1, 1024, 0, c->stream>>>(c->d_state, io.out_count, c->d_prefix[c->cur ^ 1], RECORD ? io.shadow_count : nullptr,
 	                                       RECORD ? c->d_shadow_prefix : nullptr, c->ntiles, c->cfg.ray_queue_buffer_size, c->tile_pixels);
 	CK(cudaGetLastError());
@@ -740,8 +859,9 @@ int bm_launch_frame(bm_context* c, float* blit, bm_ray* queue, bm_ray* queue2, b
 		rc = launch_upload(c);
 		if (rc) return rc;
 	}
-	CK(cudaMemsetAsync(&c->d_state->done, 0, 4, c->stream));
-	CK(cudaMemsetAsync(&c->d_state->target_paths, 0, 8, c->stream));
+	begin_kernel<<<1, 1, 0, c->stream>>>(c->d_state, 0ull);
+	CK(cudaGetLastError());
+	c->launches += 1;
 	FrameIO io{};
 	io.st = c->d_state;
 	if (c->private_valid) {
@@ -779,9 +899,9 @@ int bm_render(bm_context* c, float* blit, uint32_t frames, uint64_t target_paths
 	CK(cudaSetDevice(c->cfg.device));
 	int rc = maybe_reset(c, blit, flags);
 	if (rc) return rc;
-	CK(cudaMemsetAsync(&c->d_state->done, 0, 4, c->stream));
-	const unsigned long long tp = target_paths;
-	CK(cudaMemcpyAsync(&c->d_state->target_paths, &tp, 8, cudaMemcpyHostToDevice, c->stream));
+	begin_kernel<<<1, 1, 0, c->stream>>>(c->d_state, (unsigned long long)target_paths);
+	CK(cudaGetLastError());
+	c->launches += 1;
 	if (!c->private_valid) {
 		// no private survivor set (first frame, or the counters were set by the caller): start from an empty one
 		CK(cudaMemsetAsync(&c->d_state->primary_ray_cnt, 0, 4, c->stream));
@@ -818,6 +938,51 @@ int bm_render_to_host(bm_context* c, float* blit, uint32_t frames, uint64_t targ
 	if (request_positions_host)
 		CK(cudaMemcpyAsync(request_positions_host, c->scene.brick_load_queue, (size_t)c->sv.queue_size * 12, cudaMemcpyDeviceToHost, c->stream));
 	CK(cudaStreamSynchronize(c->stream));
+	return 0;
+}
+
+int bm_requests_pack(bm_context* c, int32_t* block) {
+	if (!c || !block) return fail_api(BM_E_INVALID, "bm_requests_pack: null argument");
+	if (!c->bound) return fail_api(BM_E_STATE, "bm_requests_pack: no scene bound (bm_scene_bind)");
+	CK(cudaSetDevice(c->cfg.device));
+	CK(cudaMemcpyAsync(block, c->scene.brick_load_queue_count, 4, cudaMemcpyDeviceToDevice, c->stream));
+	CK(cudaMemcpyAsync(block + 1, c->scene.brick_load_queue, (size_t)c->sv.queue_size * 12, cudaMemcpyDeviceToDevice, c->stream));
+	return 0;
+}
+
+int bm_requests_merge(bm_context* c, const int32_t* gathered, int world) {
+	if (!c || !gathered || world < 1) return fail_api(BM_E_INVALID, "bm_requests_merge: bad argument");
+	if (!c->bound) return fail_api(BM_E_STATE, "bm_requests_merge: no scene bound (bm_scene_bind)");
+	CK(cudaSetDevice(c->cfg.device));
+	const size_t smem = (size_t)world * c->sv.queue_size * 4 * sizeof(int32_t);
+	if (smem > 200 * 1024) return fail_api(BM_E_INVALID, "bm_requests_merge: world_size * queue_size too large for one block");
+	CK(cudaFuncSetAttribute(requests_merge_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+	requests_merge_kernel<<<1, 1024, smem, c->stream>>>(c->sv, gathered, world);
+	CK(cudaGetLastError());
+	c->launches += 1;
+	return 0;
+}
+
+int bm_kernel_timing(bm_context* c, int enable) {
+	if (!c) return fail_api(BM_E_INVALID, "bm_kernel_timing: null context");
+	CK(cudaSetDevice(c->cfg.device));
+	const int rc = drain_events(c);
+	if (rc) return rc;
+	c->timing = enable != 0;
+	c->timed_ms = 0;
+	c->timed_launches = 0;
+	return 0;
+}
+
+int bm_kernel_time(bm_context* c, double* ms_sum, uint64_t* launches) {
+	if (!c || !ms_sum || !launches) return fail_api(BM_E_INVALID, "bm_kernel_time: null argument");
+	CK(cudaSetDevice(c->cfg.device));
+	const int rc = drain_events(c);
+	if (rc) return rc;
+	*ms_sum = c->timed_ms;
+	*launches = c->timed_launches;
+	c->timed_ms = 0;
+	c->timed_launches = 0;
 	return 0;
 }
 

@@ -210,6 +210,15 @@ class Renderer:
     def reset_stats(self):
         check(self.lib.bm_reset_stats(self.h), "bm_reset_stats")
 
+    def kernel_timing(self, enable=True):
+        check(self.lib.bm_kernel_timing(self.h, 1 if enable else 0), "bm_kernel_timing")
+
+    def kernel_time(self):
+        """(summed frame-kernel milliseconds, launches) since the last read; CUDA events on the library's stream."""
+        ms, n = C.c_double(), C.c_uint64()
+        check(self.lib.bm_kernel_time(self.h, C.byref(ms), C.byref(n)), "bm_kernel_time")
+        return float(ms.value), int(n.value)
+
     def launch_kernels(self, state, flags=FRAME_DEFAULT):
         """One reference frame on the caller's State; the caller swaps the ray buffers afterwards (main.cpp:142-146)."""
         check(self.lib.bm_launch_frame(self.h, state.blit_buffer.data_ptr(), state.ray_buffer_work.data_ptr(), state.ray_buffer_next.data_ptr(),

@@ -170,9 +170,26 @@ int bm_render(bm_context* ctx, float* blit_buffer_device, uint32_t frames, uint6
 int bm_render_to_host(bm_context* ctx, float* blit_buffer_device, uint32_t frames, uint64_t target_paths, uint32_t flags,
                       float* accum_host, uint32_t* request_count_host, int32_t* request_positions_host);
 
+/* Per-launch device timing of the frame kernel (the dominant kernel) with CUDA events on the context's stream:
+ * enable, run, then read the summed duration and the number of launches it covers (the read synchronises
+ * and restarts the sum). */
+int bm_kernel_timing(bm_context* ctx, int enable);
+int bm_kernel_time(bm_context* ctx, double* ms_sum, uint64_t* launches);
+
 /* Request queue read-back (what Scene::process_load_queue copies to the host, Scene.cpp:202-209): count (may
  * exceed queue_size) and queue_size * 3 ints of cell coordinates, into HOST memory. Synchronises the stream. */
 int bm_read_requests(bm_context* ctx, uint32_t* count_host, int32_t* positions_host);
+
+/* ---- multi-GPU request exchange (not in the reference, which is single-GPU) ------------------
+ * Every GPU renders its own image tile against a full replica of the brick store; the only state that must
+ * agree between replicas is which bricks get streamed in, in which order (slot numbers are handed out in queue
+ * order, Scene.cpp:224-225). Per frame each rank packs its request block {count, positions[queue_size][3]}
+ * (1 + 3*queue_size int32), the blocks are all-gathered (NCCL), and every rank applies the same merge:
+ * blocks in rank order, entries in queue order, duplicates dropped, at most queue_size kept. The merged list
+ * replaces the local queue; the requested bit (variables.h:33) is set on cells requested by other ranks and
+ * cleared on local requests that did not make the cut (the overflow path of voxel.cuh:237-240). */
+int bm_requests_pack(bm_context* ctx, int32_t* block_device);
+int bm_requests_merge(bm_context* ctx, const int32_t* gathered_blocks_device, int world_size);
 
 /* Stream the context launches on (cudaStream_t as void*). */
 void* bm_stream(bm_context* ctx);

@@ -296,6 +296,12 @@ class Reference:
         L.ref_run_frames.argtypes = [C.c_int, C.c_int, C.c_void_p, C.c_void_p]
         L.ref_eval_sky.argtypes = [C.c_int, C.c_void_p, C.c_int, C.c_void_p]
         L.ref_host_supercell.argtypes = [C.c_int, C.c_void_p, C.c_void_p]
+        for name in ("ref_read_accum", "ref_read_counters", "ref_write_counters", "ref_sun_direction", "ref_read_indices", "ref_get_scene", "ref_get_state",
+                     "ref_host_brick_counts", "ref_alpha_sum", "ref_upload_sun" and "ref_constants"):
+            getattr(L, name).argtypes = [C.c_void_p]
+        L.ref_read_load_queue.argtypes = [C.c_void_p, C.c_void_p]
+        L.ref_init.argtypes = [C.c_int, C.c_int, C.c_int]
+        L.ref_frame.argtypes = [C.c_int]
         self._chk(L.ref_init(device, width, height))
 
     @staticmethod
@@ -394,6 +400,15 @@ class Reference:
         out = np.zeros((self.height, self.width, 4), np.float32)
         self._chk(self.lib.ref_read_accum(out.ctypes.data))
         return out
+
+    def alpha_sum(self):
+        v = C.c_double()
+        self._chk(self.lib.ref_alpha_sum(C.byref(v)))
+        return float(v.value)
+
+    def mark_sun_changed(self):
+        """sun_position_changed = true: the next launch_kernels resets the accumulation (kernel.cu:389-403)."""
+        self.lib.ref_mark_sun_changed()
 
     def clear_accum(self):
         self._chk(self.lib.ref_clear_accum())

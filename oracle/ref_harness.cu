@@ -52,6 +52,15 @@ __global__ void harness_eval_sky(int n, const float* dirs, int mode, float* out)
 	out[3 * i] = c.x; out[3 * i + 1] = c.y; out[3 * i + 2] = c.z;
 }
 
+// sum of the alpha channel of the accumulation buffer = number of finished paths (kernel.cu:301,322); used by the
+// benchmark's reference arm to find how many frames make N samples per pixel. Harness glue, not the algorithm.
+__global__ void harness_alpha_sum(const glm::vec4* buf, size_t n, double* out) {
+	double acc = 0.0;
+	for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) acc += buf[i].a;
+	for (int o = 16; o > 0; o >>= 1) acc += __shfl_down_sync(0xFFFFFFFFu, acc, o);
+	if ((threadIdx.x & 31) == 0) atomicAdd(out, acc);
+}
+
 namespace {
 State* g_state = nullptr;
 Scene* g_scene = nullptr;
@@ -267,6 +276,16 @@ int ref_write_shadow(const void* in, size_t first, size_t n) {
 int ref_read_accum(float* out) {
 	HCHECK(cudaDeviceSynchronize());
 	HCHECK(cudaMemcpy(out, g_state->blit_buffer, g_state->screen_width * g_state->screen_height * sizeof(glm::vec4), cudaMemcpyDeviceToHost));
+	return 0;
+}
+int ref_alpha_sum(double* out_host) {
+	double* d = nullptr;
+	HCHECK(cudaMalloc(&d, sizeof(double)));
+	HCHECK(cudaMemset(d, 0, sizeof(double)));
+	harness_alpha_sum<<<592, 256>>>(g_state->blit_buffer, g_state->screen_width * g_state->screen_height, d);
+	HCHECK(cudaGetLastError());
+	HCHECK(cudaMemcpy(out_host, d, sizeof(double), cudaMemcpyDeviceToHost));
+	cudaFree(d);
 	return 0;
 }
 int ref_clear_accum() {

@@ -1,0 +1,400 @@
+"""GPU parity tests proper: the CUDA product (through the C ABI, include/brickmap_b200.h) against
+  (1) the CPU oracle on the same seeded inputs, bit for bit on every geometric quantity, 1e-4 relative on radiance
+      (BASELINE.json north_star tolerance),
+  (2) the committed golden vectors produced by the unmodified reference kernels (tests/golden/),
+  (3) the unmodified reference kernels run live in the same process when oracle/_ref/*.so is present, including the
+      product running directly on the REFERENCE host's own GPUScene (true drop-in: per-superchunk cudaMalloc'd arrays).
+"""
+import hashlib
+
+import numpy as np
+import pytest
+import torch
+
+import brickmap_b200 as bm
+from brickmap_b200 import renderer as R
+from helpers import assert_close_rel, assert_records_equal, bits, max_rel_err, tile_means
+from oracle import binding as ob
+
+pytestmark = pytest.mark.gpu
+RADIANCE_TOL = 1e-4
+
+
+def cfg_from_golden(g, **kw):
+    return bm.default_config(grid_size=int(g["grid_size"]), grid_height=int(g["grid_height"]), lod_distance_2x2x2=int(g["lod2"]),
+                             lod_distance_8x8x8=int(g["lod8"]), brick_load_queue_size=int(g["queue_size"]), ray_queue_buffer_size=int(g["n_slots"]),
+                             screen_width=int(g["width"]), screen_height=int(g["height"]), **kw)
+
+
+def renderer_for(g, store, cfg=None):
+    ren = bm.Renderer(cfg or store.cfg, store)
+    ren.set_camera(bm.make_camera(position=g["cam_pos"], direction=g["cam_dir"]))
+    ren.set_sun(float(g["sun"][0]), float(g["sun"][1]))
+    return ren
+
+
+def oracle_renderer(oracle, g, resident=True):
+    s = ob.OracleScene(oracle, int(g["grid_size"]), int(g["grid_height"]), int(g["lod2"]), int(g["lod8"]), int(g["queue_size"])).generate_terrain()
+    s.set_residency(resident)
+    cam = ob.make_camera(position=g["cam_pos"], direction=g["cam_dir"])
+    return s, ob.OracleRenderer(s, int(g["width"]), int(g["height"]), int(g["n_slots"]), cam, tuple(float(v) for v in g["sun"]))
+
+
+@pytest.fixture(scope="module")
+def stores(lib, golden):
+    cache = {}
+
+    def get(name, resident=True, nonflat=False):
+        key = (name, resident, nonflat)
+        if key not in cache:
+            cache[key] = bm.SceneStore(cfg_from_golden(golden(name)), resident=resident, nonflat=nonflat)
+        return cache[key]
+    yield get
+    for s in cache.values():
+        s.close()
+
+
+# ---- scene generation on the device ------------------------------------------------------------------------------
+@pytest.mark.parametrize("variant", ["256", "4096"])
+def test_device_scene_generation_matches_reference_golden(golden, stores, variant):
+    g, s = golden(variant), stores(variant)
+    h = hashlib.sha256()
+    counts = []
+    for sc in range(s.superchunks):
+        h.update(s.indices(sc, host_view=True).tobytes())
+        h.update(s.bricks(sc).tobytes())
+        counts.append(s.brick_count(sc))
+    assert np.array_equal(np.array(counts, np.uint32), g["brick_counts"])
+    assert h.hexdigest() == str(g["scene_sha256"]), "device-generated world differs from the reference host's Scene::generate"
+    assert np.array_equal(s.indices(0), g["sc0_indices"])  # resident view == host view
+
+
+def test_unloaded_device_view(golden, stores):
+    s = stores("256", resident=False)
+    host, dev = s.indices(3, host_view=True), s.indices(3)
+    want = np.where(host & 0x80000000, 0x40000000 | (host & 0xFF000), 0).astype(np.uint32)  # Scene.cpp:158-164
+    assert np.array_equal(dev, want)
+
+
+# ---- sky ----------------------------------------------------------------------------------------------------------
+def test_sky_matches_reference_golden(golden, stores):
+    g = golden("256")
+    ren = renderer_for(g, stores("256"))
+    for mode, nm in enumerate(("sun", "sky", "sunsky")):
+        assert_close_rel(ren.eval_sky(g["sky_dirs"], mode), g["sky_" + nm], RADIANCE_TOL, nm)
+
+
+def test_sky_other_sun_positions_match_oracle(oracle, golden, stores):
+    g = golden("256")
+    ren = renderer_for(g, stores("256"))
+    for sun in ((0.3, 0.2), (0.7, 0.45), (0.05, 0.49)):
+        ren.set_sun(*sun)
+        sd = np.zeros(3, np.float32)
+        oracle.lib.orc_sun_direction(sun[0], sun[1], sd.ctypes.data)
+        for mode in range(3):
+            assert_close_rel(ren.eval_sky(g["sky_dirs"], mode), ob.sky_eval(oracle, g["sky_dirs"], mode, sd), RADIANCE_TOL, "sun %s mode %d" % (sun, mode))
+
+
+# ---- traversal ----------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("variant,nonflat", [("256", False), ("256", True), ("256lod", False), ("256lod", True), ("4096", False)])
+def test_traversal_matches_reference_golden(golden, stores, variant, nonflat):
+    g = golden(variant)
+    ren = renderer_for(g, stores(variant, nonflat=nonflat))
+    n = g["trace_origins"].shape[0]
+    hit, dist, nrm = ren.trace(g["trace_origins"], g["trace_directions"], distances=np.full(n, 1e20, np.float32))
+    assert np.array_equal(bits(dist), bits(g["trace_distance"]))
+    assert np.array_equal(bits(nrm), bits(g["trace_normal"]))
+    assert int(hit.sum()) == int((g["trace_distance"] < 1e20).sum()) > 0
+
+
+def test_traversal_edge_cases_match_oracle(oracle, golden, stores):
+    """Axis-aligned and zero-component directions, origins on cell/voxel boundaries, on the world faces, outside the world,
+    empty input."""
+    g = golden("256lod")
+    ren = renderer_for(g, stores("256lod"))
+    s, _ = oracle_renderer(oracle, g)
+    rng = np.random.default_rng(7)
+    n = 20000
+    o = rng.uniform(-40, 300, size=(n, 3)).astype(np.float32)
+    d = rng.normal(size=(n, 3)).astype(np.float32)
+    o[:4000] = np.round(o[:4000] / 8) * 8          # on cell boundaries
+    o[4000:8000] = np.round(o[4000:8000])          # on voxel boundaries
+    o[8000:9000, 2] = 256.0                        # on the top face
+    o[9000:10000, 0] = 0.0
+    d[10000:12000, rng.integers(0, 3)] = 0.0
+    d[12000:13000] = np.eye(3, dtype=np.float32)[rng.integers(0, 3, 1000)] * rng.choice([-1.0, 1.0], size=(1000, 1)).astype(np.float32)
+    d /= np.linalg.norm(d, axis=1, keepdims=True)
+    cam_cell = [int(v / 8.0) for v in g["cam_pos"]]
+    nrm0 = rng.choice([-1.0, 0.0, 1.0], size=(n, 3)).astype(np.float32)
+    oh, od, on = s.trace(o, d, cam_cell, normals=nrm0, distances=np.full(n, 1e20, np.float32), threads=0)
+    mh, md, mn = ren.trace(o, d, normals=nrm0, distances=np.full(n, 1e20, np.float32))
+    assert np.array_equal(mh, oh) and np.array_equal(bits(md), bits(od)) and np.array_equal(bits(mn), bits(on))
+    eh, ed, en = ren.trace(np.zeros((0, 3), np.float32), np.zeros((0, 3), np.float32))
+    assert eh.shape == (0,) and ed.shape == (0,)
+
+
+# ---- whole frames ----------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("variant,nonflat", [("256", False), ("256lod", True), ("4096", False)])
+def test_launch_frame_matches_reference_golden(golden, stores, variant, nonflat):
+    """bm_launch_frame == launch_kernels: every buffer the reference leaves behind, frame after frame."""
+    g = golden(variant)
+    store = stores(variant, nonflat=nonflat)
+    ren = renderer_for(g, store)
+    state = bm.State(store.cfg)
+    f = 1
+    while "f%d_counters" % f in g:
+        p = "f%d_" % f
+        ren.launch_kernels(state)
+        c = ren.counters()
+        assert [c.primary_ray_cnt, c.shadow_ray_cnt, c.start_position, c.frame] == [int(v) for v in g[p + "counters"]] + [f + 1]
+        ext = state.rays("work")
+        assert int((ext["distance"] < 1e20).sum()) == int(g[p + "ext_hits"])
+        assert_records_equal(ext[g[p + "ext_idx"]], g[p + "ext"], what="frame %d post-extend" % f)
+        assert_records_equal(state.rays("next", c.primary_ray_cnt)[g[p + "next_idx"]], g[p + "next"], what="frame %d survivors" % f)
+        sh = state.shadows(c.shadow_ray_cnt)[g[p + "shadow_idx"]]
+        assert_records_equal(sh, g[p + "shadow"], fields=("origin", "direction", "pixel_index"), what="frame %d shadow rays" % f)
+        assert_close_rel(sh["color"], g[p + "shadow"]["color"], RADIANCE_TOL, "frame %d shadow colour" % f)
+        acc = state.blit_buffer.cpu().numpy()
+        assert_close_rel(acc.reshape(-1, 4)[g["accum_pix"]], g[p + "accum_val"], RADIANCE_TOL, "frame %d accumulation samples" % f)
+        assert_close_rel(tile_means(acc), g[p + "accum_tiles"], RADIANCE_TOL, "frame %d tile means" % f)
+        assert abs(float(acc[..., 3].astype(np.float64).sum()) - float(g[p + "alpha_sum"])) < 0.5
+        state.swap()  # main.cpp:146
+        f += 1
+    assert f > 2
+
+
+def test_fused_render_matches_oracle_over_many_frames(oracle, golden, stores):
+    """bm_render (private ray state, no per-stage records) == the oracle's canonical wavefront loop, 8 frames."""
+    g = golden("256")
+    store = stores("256")
+    ren = renderer_for(g, store)
+    _, oren = oracle_renderer(oracle, g)
+    blit = torch.zeros(int(g["height"]), int(g["width"]), 4, dtype=torch.float32, device="cuda")
+    frames = 8
+    ren.render(blit, 3)
+    ren.render(blit, frames - 3)  # state carries over between calls
+    for _ in range(frames):
+        oren.frame()
+    c = ren.counters()
+    assert [c.primary_ray_cnt, c.start_position, c.frame] == [oren.state.primary_ray_cnt, oren.state.start_position, oren.state.frame]
+    st = ren.stats()
+    assert st["frames"] == frames and st["extend_rays"] == frames * int(g["n_slots"])
+    assert st["extend_rays"] + st["shadow_rays"] == oren.stats.rays
+    assert st["terminations"] == oren.stats.terminations and st["unoccluded"] == oren.stats.unoccluded
+    acc = blit.cpu().numpy()
+    assert np.array_equal(acc[..., 3], oren.accum[..., 3]), "alpha (finished paths per pixel) must match exactly"
+    assert_close_rel(acc, oren.accum, RADIANCE_TOL, "accumulated radiance after %d frames" % frames)
+    # a frame through the reference-compatible entry point continues from the private state of the fused path
+    state = bm.State(store.cfg)
+    state.blit_buffer.copy_(blit)
+    ren.launch_kernels(state, flags=R.FRAME_NO_RESET)
+    oren.frame()
+    c = ren.counters()
+    assert_records_equal(state.rays("next", c.primary_ray_cnt), oren.rays[: c.primary_ray_cnt], what="survivors after mixing both entry points")
+
+
+def test_work_counters_match_oracle(oracle, golden, stores):
+    """S (cell steps), K (bricks entered), P, V of SURVEY 8d, which feed the roofline's algorithmic bytes."""
+    g = golden("256")
+    ren = renderer_for(g, stores("256"))
+    _, oren = oracle_renderer(oracle, g)
+    blit = torch.zeros(int(g["height"]), int(g["width"]), 4, dtype=torch.float32, device="cuda")
+    ren.render(blit, 2, flags=R.FRAME_COUNT_WORK)
+    oren.frame()
+    oren.frame()
+    st, os_ = ren.stats(), oren.stats.as_dict()
+    assert st["cell_steps"] == os_["index_reads"] and st["bricks_entered"] == os_["bricks"]
+    assert st["index_reads"] <= st["cell_steps"]
+    assert st["terminations"] == os_["terminations"] and st["unoccluded"] == os_["unoccluded"]
+
+
+def test_render_target_and_reset(golden, stores):
+    g = golden("256")
+    ren = renderer_for(g, stores("256"))
+    pixels = int(g["height"]) * int(g["width"])
+    blit = torch.zeros(int(g["height"]), int(g["width"]), 4, dtype=torch.float32, device="cuda")
+    ren.render(blit, 200, target_paths=2 * pixels)  # stops on the device once 2 spp are reached
+    st = ren.stats()
+    assert 2 * pixels <= st["terminations"] < 2 * pixels + 2 * int(g["n_slots"]) and st["frames"] < 50
+    assert float(blit[..., 3].sum()) == st["terminations"]
+    ren.set_sun(0.3, 0.2)  # sun move -> accumulation reset (kernel.cu:389-403); cursor and frame number are kept
+    before = ren.counters()
+    ren.render(blit, 1)
+    after = ren.counters()
+    assert after.frame == before.frame + 1
+    assert float(blit[..., 3].sum()) == ren.stats()["terminations"] - st["terminations"]
+
+
+def test_tiles_compose_like_independent_renderers(oracle, golden):
+    """Multi-GPU partition: a context restricted to a row band equals the oracle run on that band's camera rays."""
+    g = golden("256")
+    w, h = int(g["width"]), int(g["height"])
+    row0, rows = bm.tile_rows_for_rank(h, 1, 2)
+    cfg = cfg_from_golden(g, tile_row0=row0, tile_rows=rows)
+    store = bm.SceneStore(cfg, resident=True)
+    ren = renderer_for(g, store, cfg)
+    blit = torch.zeros(rows, w, 4, dtype=torch.float32, device="cuda")
+    ren.render(blit, 2)
+    acc = blit.cpu().numpy()
+    assert acc.shape == (rows, w, 4) and acc[..., 3].sum() == ren.stats()["terminations"]
+    # full-image run: the band's first-frame primaries see the same geometry -> same hit mask in the band
+    cfg_full = cfg_from_golden(g)
+    ren_full = renderer_for(g, bm.SceneStore(cfg_full, resident=True), cfg_full)
+    st_full = bm.State(cfg_full)
+    ren_full.launch_kernels(st_full)
+    st_band = bm.State(cfg)
+    ren_band = renderer_for(g, store, cfg)
+    ren_band.launch_kernels(st_band)
+    full, band = st_full.rays("work"), st_band.rays("work")
+    # slot i of the band renders pixel (i % w, row0 + i // w): same pixel as slot i + row0*w of the full image, other jitter seed
+    n = min(rows * w, len(band))
+    assert np.array_equal(band["pixel_index"][:n], np.arange(n, dtype=np.uint32))
+    assert np.array_equal(full["pixel_index"][row0 * w: row0 * w + 8], np.arange(row0 * w, row0 * w + 8, dtype=np.uint32))
+    agree = ((band["distance"][:n] < 1e20) == (full["distance"][row0 * w: row0 * w + n] < 1e20)).mean()
+    assert agree > 0.99, "band and full image disagree on hit/miss for %.2f%% of pixels" % (100 * (1 - agree))
+
+
+# ---- streaming ----------------------------------------------------------------------------------------------------
+def test_streaming_matches_oracle_as_sets(oracle, golden, stores):
+    """From an empty device scene: requests (as sorted sets, P4 of SURVEY 8c), index words modulo slot numbers, radiance."""
+    g = golden("256")
+    cfg = cfg_from_golden(g)
+    store = bm.SceneStore(cfg, resident=False)
+    ren = renderer_for(g, store, cfg)
+    s, oren = oracle_renderer(oracle, g, resident=False)
+    state = bm.State(cfg)
+    for f in range(1, 7):
+        ren.launch_kernels(state)  # includes the upload of what the previous frame requested (kernel.cu:407-414)
+        cnt, pos = ren.load_queue()
+        store.process_load_queue(ren.stream)  # Scene.cpp:200
+        state.swap()
+        if f > 1:
+            s.stream()
+        oren.frame(threads=1)
+        ocnt, opos = s.queue()
+        assert cnt == ocnt, "frame %d: %d requests vs oracle %d" % (f, cnt, ocnt)
+        if cnt <= int(g["queue_size"]):
+            assert sorted(map(tuple, pos)) == sorted(map(tuple, opos)), "frame %d request sets differ" % f
+        else:
+            assert len(set(map(tuple, pos))) == len(pos) == int(g["queue_size"])
+        c = ren.counters()
+        assert [c.primary_ray_cnt, c.shadow_ray_cnt] == [oren.state.primary_ray_cnt, oren.state.shadow_ray_cnt]
+    ren.synchronize()
+    for sc in range(store.superchunks):
+        mine, want = store.indices(sc), s.gpu_indices(sc)
+        assert np.array_equal(mine & ~np.uint32(0xFFF), want & ~np.uint32(0xFFF)), "index words (slot bits masked) differ in superchunk %d" % sc
+        loaded = np.flatnonzero(mine & 0x80000000)
+        if loaded.size:
+            gb = store.bricks(sc, gpu_view=True)
+            for cell in loaded[:: max(1, loaded.size // 16)]:
+                assert np.array_equal(gb[mine[cell] & 0xFFF], s.gpu_brick(sc, int(want[cell] & 0xFFF))), "brick content through the indirection"
+    assert_close_rel(state.blit_buffer.cpu().numpy(), oren.accum, RADIANCE_TOL, "accumulation while streaming")
+
+
+def test_streaming_serial_order_matches_reference_golden(golden):
+    """Frame 1 of the reference's streaming fixture: the request SET of an all-unloaded scene."""
+    g = golden("256")
+    cfg = cfg_from_golden(g)
+    store = bm.SceneStore(cfg, resident=False)
+    ren = renderer_for(g, store, cfg)
+    state = bm.State(cfg)
+    ren.launch_kernels(state)
+    cnt, pos = ren.load_queue()
+    assert cnt == int(g["stream1_count"])
+    assert sorted(map(tuple, pos)) == sorted(map(tuple, g["stream1_positions"]))
+
+
+def test_request_merge_kernel_matches_specification(golden):
+    """bm_requests_merge (CUDA) == brickmap_b200.parallel.merge_request_blocks (the specification the gloo test uses)."""
+    import ctypes as C
+    from brickmap_b200.parallel import merge_request_blocks
+    g = golden("256")
+    cfg = cfg_from_golden(g)
+    q = cfg.brick_load_queue_size
+    store = bm.SceneStore(cfg, resident=False)
+    ren = renderer_for(g, store, cfg)
+    rng = np.random.default_rng(3)
+    # candidate cells: non-empty ones, taken from the reference's own request list
+    cells = np.concatenate([g["stream1_positions"], g["stream2_positions"], g["stream3_positions"]])
+    world = 3
+    blocks = np.zeros((world, 1 + 3 * q), np.int32)
+    for r in range(world):
+        pick = cells[rng.choice(len(cells), size=[700, 300, 600][r], replace=False)]
+        blocks[r, 0] = len(pick)
+        blocks[r, 1:1 + 3 * len(pick)] = pick.reshape(-1)
+    total, kept, dropped = merge_request_blocks(blocks, q)
+    assert total > q and len(dropped) > 0
+    dev = torch.as_tensor(blocks, device="cuda")
+    lib = bm.load()
+    assert lib.bm_requests_merge(ren.h, dev.data_ptr(), world) == 0
+    cnt, pos = ren.load_queue()
+    assert cnt == total and np.array_equal(pos, kept)
+    idx = {sc: store.indices(sc) for sc in range(store.superchunks)}
+
+    def word(p):
+        sc = (p[0] >> 4) + (p[1] >> 4) * (cfg.grid_size // 128) + (p[2] >> 4) * (cfg.grid_size // 128) ** 2
+        return idx[sc][(p[0] & 15) + (p[1] & 15) * 16 + (p[2] & 15) * 256]
+    assert all(word(p) & 0x20000000 for p in kept), "kept requests carry the requested bit"
+    assert not any(word(p) & 0x20000000 for p in dropped), "dropped requests are released for a later frame"
+
+
+# ---- against the live reference -------------------------------------------------------------------------------------
+@pytest.mark.skipif(not ob.Reference.available("256"), reason="oracle/_ref not built")
+def test_drop_in_on_the_reference_hosts_own_scene(golden):
+    """The reference's Scene (host code, Scene.cpp) owns the device scene; our kernels run on ITS GPUScene pointers, through
+    the pointer tables of separately cudaMalloc'd superchunks, next to the reference's own kernels."""
+    g = golden("256")
+    ref = ob.Reference("256", int(g["width"]), int(g["height"]))
+    ref.generate()
+    ref.force_resident()
+    cam = ob.make_camera(position=g["cam_pos"], direction=g["cam_dir"])
+    ref.set_camera(cam)
+    ref.set_sun(0.05, 0.1)
+    ref.upload_sun()
+    cfg = cfg_from_golden(g)
+    ren = bm.Renderer(cfg, bm.GpuScene(*ref.scene_pointers()))
+    ren.set_camera(bm.make_camera(position=g["cam_pos"], direction=g["cam_dir"]))
+    ren.set_sun(0.05, 0.1)
+    state = bm.State(cfg)
+    ref.clear_accum()
+    ref.write_counters(primary_ray_cnt=0, start_position=0, raynr_primary=0, raynr_extend=0, raynr_shade=0, raynr_connect=0, shadow_ray_cnt=0)
+    for f in (1, 2):
+        ref.run_stage("primary_rays", frame=f)
+        ref.run_stage("set_wavefront_globals")
+        ref.run_stage("extend", frame=f)
+        r_ext = ref.read_rays(0)
+        ref.run_stage("shade", frame=f, serial=True)
+        rc = ref.counters()
+        r_next = ref.read_rays(1, 0, rc["primary_ray_cnt"])
+        ref.run_stage("connect", frame=f)
+        ref.swap_buffers()
+        ren.launch_kernels(state)
+        c = ren.counters()
+        assert c.primary_ray_cnt == rc["primary_ray_cnt"] and c.shadow_ray_cnt == rc["shadow_ray_cnt"]
+        assert_records_equal(state.rays("work"), r_ext, what="frame %d post-extend vs live reference" % f)
+        assert_records_equal(state.rays("next", c.primary_ray_cnt), r_next, what="frame %d survivors vs live reference" % f)
+        state.swap()
+    assert_close_rel(state.blit_buffer.cpu().numpy(), ref.read_accum(), RADIANCE_TOL, "accumulation vs live reference")
+
+
+@pytest.mark.skipif(not ob.Reference.available("256"), reason="oracle/_ref not built")
+def test_statistical_parity_with_reference_parallel_run(golden, stores):
+    """P3 of SURVEY 8c: the reference's normal (parallel, non-deterministic after frame 1) run and ours converge to the
+    same image: tile means of the 40-frame averages agree within Monte-Carlo noise."""
+    g = golden("256")
+    w, h = int(g["width"]), int(g["height"])
+    ref = ob.Reference("256", w, h)
+    ref.generate()
+    ref.force_resident()
+    ref.set_camera(ob.make_camera(position=g["cam_pos"], direction=g["cam_dir"]))
+    ref.set_sun(0.05, 0.1)
+    ref.run_frames(40)
+    r = ref.read_accum()
+    ren = renderer_for(g, stores("256"))
+    blit = torch.zeros(h, w, 4, dtype=torch.float32, device="cuda")
+    ren.render(blit, 40)
+    m = blit.cpu().numpy()
+    assert abs(m[..., 3].sum() / r[..., 3].sum() - 1) < 0.01
+    rm, mm = tile_means(r), tile_means(m)
+    rel = np.abs(mm[..., :3] / mm[..., 3:] - rm[..., :3] / rm[..., 3:]) / np.maximum(rm[..., :3] / rm[..., 3:], 1e-6)
+    assert np.median(rel) < 0.02 and rel.max() < 0.15, "tile means differ: median %.3f max %.3f" % (np.median(rel), rel.max())
