@@ -600,7 +600,9 @@ int bm_create(bm_context** out, const bm_config* cfg) {
 	cudaDeviceProp props;
 	CKC(cudaGetDeviceProperties(&props, cfg->device));
 	c->sm_count = props.multiProcessorCount;
-	CKC(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
+	// a BLOCKING stream, like the reference's kernel_stream (cudaStreamCreate, Scene.cpp:35): work a host enqueues on the
+	// legacy default stream (the reference's staging copies, Scene.cpp:228-229; torch's default stream) is ordered with ours
+	CKC(cudaStreamCreate(&c->stream));
 	CKC(cudaMalloc(&c->d_state, sizeof(DeviceState)));
 	CKC(cudaMemset(c->d_state, 0, sizeof(DeviceState)));
 	const uint32_t one = 1;

@@ -269,9 +269,13 @@ class Reference:
     """The unmodified reference kernels behind oracle/ref_harness.cu. Needs a GPU and a prebuilt oracle/_ref library."""
 
     VARIANTS = ("4096", "256", "256lod")
+    # "dropin_256": the reference HOST code (Scene.cpp, State, main-loop body) linked against integration/launch_kernels_dropin.cpp
+    # and libbrickmap_b200.so instead of kernel.cu/sunsky.cu; only the host-level entry points exist in that library.
 
     @staticmethod
     def path(variant):
+        if variant.startswith("dropin_"):
+            return os.path.join(HERE, "_ref", "libbrickmap_%s.so" % variant)
         return os.path.join(HERE, "_ref", "libbrickmap_ref_%s.so" % variant)
 
     @classmethod
@@ -292,12 +296,15 @@ class Reference:
         L.ref_write_shadow.argtypes = [C.c_void_p, C.c_size_t, C.c_size_t]
         L.ref_set_camera.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_float, C.c_float]
         L.ref_set_sun.argtypes = [C.c_float, C.c_float]
-        L.ref_run_stage.argtypes = [C.c_int, C.c_int, C.c_uint, C.c_int]
         L.ref_run_frames.argtypes = [C.c_int, C.c_int, C.c_void_p, C.c_void_p]
-        L.ref_eval_sky.argtypes = [C.c_int, C.c_void_p, C.c_int, C.c_void_p]
         L.ref_host_supercell.argtypes = [C.c_int, C.c_void_p, C.c_void_p]
-        for name in ("ref_read_accum", "ref_read_counters", "ref_write_counters", "ref_sun_direction", "ref_read_indices", "ref_get_scene", "ref_get_state",
-                     "ref_host_brick_counts", "ref_alpha_sum", "ref_upload_sun" and "ref_constants"):
+        if not variant.startswith("dropin_"):
+            L.ref_run_stage.argtypes = [C.c_int, C.c_int, C.c_uint, C.c_int]
+            L.ref_eval_sky.argtypes = [C.c_int, C.c_void_p, C.c_int, C.c_void_p]
+            L.ref_read_counters.argtypes = [C.c_void_p]
+            L.ref_write_counters.argtypes = [C.c_void_p]
+        for name in ("ref_read_accum", "ref_sun_direction", "ref_read_indices", "ref_get_scene", "ref_get_state", "ref_host_brick_counts", "ref_alpha_sum",
+                     "ref_constants"):
             getattr(L, name).argtypes = [C.c_void_p]
         L.ref_read_load_queue.argtypes = [C.c_void_p, C.c_void_p]
         L.ref_init.argtypes = [C.c_int, C.c_int, C.c_int]

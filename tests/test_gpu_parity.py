@@ -398,3 +398,35 @@ def test_statistical_parity_with_reference_parallel_run(golden, stores):
     rm, mm = tile_means(r), tile_means(m)
     rel = np.abs(mm[..., :3] / mm[..., 3:] - rm[..., :3] / rm[..., 3:]) / np.maximum(rm[..., :3] / rm[..., 3:], 1e-6)
     assert np.median(rel) < 0.02 and rel.max() < 0.15, "tile means differ: median %.3f max %.3f" % (np.median(rel), rel.max())
+
+
+@pytest.mark.skipif(not (ob.Reference.available("256") and ob.Reference.available("dropin_256")), reason="oracle/_ref not built")
+def test_reference_host_main_loop_on_new_kernels(golden, tmp_path):
+    """integration/launch_kernels_dropin.cpp: the reference's own host code (Scene::generate, State, launch_kernels call,
+    Scene::process_load_queue with its pinned staging buffers and growing brick arrays, buffer swap: main.cpp:142-146) runs
+    unchanged on top of libbrickmap_b200.so. Compared with the same loop on the reference's kernels: frame 1 is deterministic
+    in both (requests as a set, accumulation to 1e-4); later frames of the reference depend on thread scheduling, so after the
+    world has streamed in only the image statistics are compared."""
+    import os
+    import subprocess
+    import sys
+    g = golden("256")
+    runs = {}
+    worker = os.path.join(os.path.dirname(os.path.abspath(__file__)), "host_loop_worker.py")
+    for variant in ("256", "dropin_256"):
+        out = str(tmp_path / ("%s.npz" % variant))
+        subprocess.run([sys.executable, worker, variant, out, "40"], check=True, timeout=600)
+        r = np.load(out)
+        runs[variant] = (int(r["count"]), r["positions"], r["accum1"], r["accum"], r["indices"])
+    (rc, rp, ra1, ra, ri), (dc, dp, da1, da, di) = runs["256"], runs["dropin_256"]
+    assert rc == dc == int(g["stream1_count"]) and sorted(map(tuple, rp)) == sorted(map(tuple, dp))
+    assert_close_rel(da1, ra1, RADIANCE_TOL, "frame 1 accumulation, reference host on new kernels vs on its own kernels")
+    # which rarely-hit bricks a random bounce ray touches differs between any two runs of the reference itself
+    r_loaded, d_loaded = (ri & 0x80000000) != 0, (di & 0x80000000) != 0
+    assert r_loaded.sum() > 1000 and (r_loaded != d_loaded).sum() < 0.03 * r_loaded.sum(), "resident brick sets diverge: %d vs %d, %d differ" % (
+        r_loaded.sum(), d_loaded.sum(), (r_loaded != d_loaded).sum())
+    assert np.array_equal(ri == 0, di == 0)
+    assert abs(da[..., 3].sum() / ra[..., 3].sum() - 1) < 0.01
+    rm, dm = tile_means(ra), tile_means(da)
+    rel = np.abs(dm[..., :3] / dm[..., 3:] - rm[..., :3] / rm[..., 3:]) / np.maximum(rm[..., :3] / rm[..., 3:], 1e-6)
+    assert np.median(rel) < 0.02 and rel.max() < 0.15
