@@ -120,6 +120,8 @@ struct SceneView {
 	uint32_t queue_size;          // variables.h:35
 	int coarse_shift, coarse_nx, coarse_nxy;  // bitmap geometry
 	uint32_t coarse_words;
+	const uint32_t* fine;         // emptiness per cell: 64 bits per 4x4x4 block, bit (x&3) | (y&3)<<2 | (z&3)<<4 (global)
+	int fine_nx, fine_nxy;        // 4x4x4 blocks per row / per slab
 };
 
 struct WorkCounters {
@@ -130,7 +132,7 @@ struct WorkCounters {
 struct Dda {
 	I3 pos;
 	I3 stepi;
-	F3 step, tmax, tdelta;
+	F3 tmax, tdelta;
 };
 
 // common set-up of voxel.cuh:27-48 / 80-101 / 158-186
@@ -138,40 +140,59 @@ __device__ __forceinline__ void dda_setup(const F3& o, const F3& d, Dda& a) {
 	a.pos = I3{ (int)o.x, (int)o.y, (int)o.z };
 	const F3 cb{ d.x > 0.f ? (float)(a.pos.x + 1) : (float)a.pos.x, d.y > 0.f ? (float)(a.pos.y + 1) : (float)a.pos.y,
 		         d.z > 0.f ? (float)(a.pos.z + 1) : (float)a.pos.z };
-	a.step = F3{ gsign(d.x), gsign(d.y), gsign(d.z) };
-	a.stepi = I3{ (int)a.step.x, (int)a.step.y, (int)a.step.z };
+	const F3 step{ gsign(d.x), gsign(d.y), gsign(d.z) };
+	a.stepi = I3{ (int)step.x, (int)step.y, (int)step.z };
+	// keep the integer steps in registers: left alone the compiler re-derives them from the direction in every DDA iteration
+	asm volatile("" : "+r"(a.stepi.x), "+r"(a.stepi.y), "+r"(a.stepi.z));
 	const F3 rdinv{ d.x == 0.0f ? 0.0f : 1.f / d.x, d.y == 0.0f ? 0.0f : 1.f / d.y, d.z == 0.0f ? 0.0f : 1.f / d.z };
 	a.tmax = F3{ d.x != 0.f ? (cb.x - o.x) * rdinv.x : 1000000.f, d.y != 0.f ? (cb.y - o.y) * rdinv.y : 1000000.f,
 		         d.z != 0.f ? (cb.z - o.z) * rdinv.z : 1000000.f };
-	a.tdelta = F3{ a.step.x * rdinv.x, a.step.y * rdinv.y, a.step.z * rdinv.z };
+	a.tdelta = F3{ step.x * rdinv.x, step.y * rdinv.y, step.z * rdinv.z };
 }
 
-// voxel.cuh:66-74 / 122-130 / 249-258. Returns false when the ray leaves through `out`.
-__device__ __forceinline__ bool dda_advance(Dda& a, const I3& out, int& step_axis) {
-	const float tx = a.tmax.x, ty = a.tmax.y, tz = a.tmax.z;
-	const bool xy = tx < ty, xz = tx < tz, yz = ty < tz;
-	step_axis = xy ? (xz ? 0 : 2) : (yz ? 1 : 2);
-	const bool mx = xy && xz;
-	const bool my = (ty <= tx) && yz;
-	const bool mz = (tz <= tx) && (tz <= ty);
-	// pos += mask * step: int(1.f * step) or int(0.f * step) = 0
-	a.pos.x += mx ? a.stepi.x : 0;
-	a.pos.y += my ? a.stepi.y : 0;
-	a.pos.z += mz ? a.stepi.z : 0;
-	if (comp(a.pos, step_axis) == comp(out, step_axis)) return false;
-	// tmax += mask * tdelta: mask is 0/1, so this is a predicated add (1 * tdelta is exact; 0 * tdelta == 0 leaves
-	// tmax unchanged for every finite tdelta, i.e. unless a direction component is a non-zero denormal < 2^-128)
-	a.tmax.x = mx ? tx + a.tdelta.x : tx;
-	a.tmax.y = my ? ty + a.tdelta.y : ty;
-	a.tmax.z = mz ? tz + a.tdelta.z : tz;
-	return true;
+// One DDA step, voxel.cuh:66-74 / 122-130 / 249-258, hand-scheduled: 3 compares, 3 predicate ops, 3 predicated integer adds,
+// 3 predicated float adds, 2 instructions for the axis. Semantics of the reference:
+//   axis  = (tx < ty) ? ((tx < tz) ? 0 : 2) : ((ty < tz) ? 1 : 2)
+//   mask  = (tx < ty && tx < tz, ty <= tx && ty < tz, tz <= tx && tz <= ty)   -- exactly one is set unless a tmax is NaN
+//   pos  += mask * step;  exit test on the stepped axis;  tmax += mask * tdelta
+// mask * tdelta is a predicated add (1 * tdelta is exact, 0 * tdelta == 0) and ty <= tx is !(tx < ty); both hold unless a
+// direction component is a non-zero denormal (< 2^-128), whose 1/d = inf makes the reference produce NaNs.
+// tmax is updated before the exit test here; on exit the caller drops this DDA's state, as the reference does.
+// `lim`: positions are in [0, lim) until the exit step, which is the reference's pos[axis] == out[axis] with out = lim or -1.
+__device__ __forceinline__ bool dda_advance(Dda& a, const I3& lim, int& step_axis) {
+	asm("{\n\t"
+	    ".reg .pred pxy, pxz, pyz, mx, my, mz;\n\t"
+	    "setp.lt.f32 pxy, %3, %4;\n\t"
+	    "setp.lt.f32 pxz, %3, %5;\n\t"
+	    "setp.lt.f32 pyz, %4, %5;\n\t"
+	    "and.pred mx, pxy, pxz;\n\t"
+	    "not.pred pxy, pxy;\n\t"
+	    "and.pred my, pxy, pyz;\n\t"
+	    "or.pred mz, mx, my;\n\t"
+	    "not.pred mz, mz;\n\t"
+	    "@mx add.s32 %0, %0, %7;\n\t"
+	    "@my add.s32 %1, %1, %8;\n\t"
+	    "@mz add.s32 %2, %2, %9;\n\t"
+	    "@mx add.rn.f32 %3, %3, %10;\n\t"
+	    "@my add.rn.f32 %4, %4, %11;\n\t"
+	    "@mz add.rn.f32 %5, %5, %12;\n\t"
+	    "selp.s32 %6, 0, 2, mx;\n\t"
+	    "@my mov.s32 %6, 1;\n\t"
+	    "}"
+	    : "+r"(a.pos.x), "+r"(a.pos.y), "+r"(a.pos.z), "+f"(a.tmax.x), "+f"(a.tmax.y), "+f"(a.tmax.z), "=r"(step_axis)
+	    : "r"(a.stepi.x), "r"(a.stepi.y), "r"(a.stepi.z), "f"(a.tdelta.x), "f"(a.tdelta.y), "f"(a.tdelta.z));
+	return (unsigned)a.pos.x < (unsigned)lim.x && (unsigned)a.pos.y < (unsigned)lim.y && (unsigned)a.pos.z < (unsigned)lim.z;
+}
+
+__device__ __forceinline__ F3 axis_normal(const Dda& a, int axis) {  // normal[step_axis] = -step[step_axis]
+	return F3{ axis == 0 ? -(float)a.stepi.x : 0.f, axis == 1 ? -(float)a.stepi.y : 0.f, axis == 2 ? -(float)a.stepi.z : 0.f };
 }
 
 // voxel.cuh:26-77 (2x2x2 LoD octants)
 __device__ __forceinline__ bool intersect_byte(const F3& origin, const F3& direction, F3& normal, float& distance, uint32_t byte) {
 	Dda a;
 	dda_setup(origin, direction, a);
-	const I3 out{ direction.x > 0.f ? 2 : -1, direction.y > 0.f ? 2 : -1, direction.z > 0.f ? 2 : -1 };
+	const I3 lim{ 2, 2, 2 };
 	a.pos = I3{ a.pos.x % 2, a.pos.y % 2, a.pos.z % 2 };
 	distance = 0.f;
 	int step_axis = -1;
@@ -179,12 +200,12 @@ __device__ __forceinline__ bool intersect_byte(const F3& origin, const F3& direc
 		const int bit = a.pos.x + a.pos.y * 2 + a.pos.z * 4;
 		if (bit >= 0 && bit < 8 && ((byte >> bit) & 1u)) {
 			if (step_axis > -1) {
-				normal = F3{ step_axis == 0 ? -a.step.x : 0.f, step_axis == 1 ? -a.step.y : 0.f, step_axis == 2 ? -a.step.z : 0.f };
+				normal = axis_normal(a, step_axis);
 				distance = comp(a.tmax, step_axis) - comp(a.tdelta, step_axis);
 			}
 			return true;
 		}
-		if (!dda_advance(a, out, step_axis)) break;
+		if (!dda_advance(a, lim, step_axis)) break;
 	}
 	return false;
 }
@@ -194,7 +215,7 @@ __device__ __forceinline__ bool intersect_byte(const F3& origin, const F3& direc
 __device__ __forceinline__ bool intersect_brick(const F3& origin, const F3& direction, F3& normal, float& distance, const bm_brick* brick) {
 	Dda a;
 	dda_setup(origin, direction, a);
-	const I3 out{ direction.x > 0.f ? 8 : -1, direction.y > 0.f ? 8 : -1, direction.z > 0.f ? 8 : -1 };
+	const I3 lim{ 8, 8, 8 };
 	a.pos = I3{ a.pos.x % 8, a.pos.y % 8, a.pos.z % 8 };
 	distance = 0.f;
 	int step_axis = -1;
@@ -205,12 +226,12 @@ __device__ __forceinline__ bool intersect_brick(const F3& origin, const F3& dire
 		// (undefined there); they are treated as empty here and in the oracle
 		if (lin >= 0 && lin < 512 && ((__ldg(words + (lin >> 5)) >> (lin & 31)) & 1u)) {
 			if (step_axis > -1) {
-				normal = F3{ step_axis == 0 ? -a.step.x : 0.f, step_axis == 1 ? -a.step.y : 0.f, step_axis == 2 ? -a.step.z : 0.f };
+				normal = axis_normal(a, step_axis);
 				distance = comp(a.tmax, step_axis) - comp(a.tdelta, step_axis);
 			}
 			return true;
 		}
-		if (!dda_advance(a, out, step_axis)) break;
+		if (!dda_advance(a, lim, step_axis)) break;
 	}
 	return false;
 }
@@ -251,15 +272,21 @@ __device__ __forceinline__ bool intersect_voxel(const SceneView& sv, const uint3
 	Dda a;
 	dda_setup(origin, direction, a);
 	if (a.pos.x < 0 || a.pos.x >= sv.cells || a.pos.y < 0 || a.pos.y >= sv.cells || a.pos.z < 0 || a.pos.z >= sv.cells_height) return false;
-	const I3 out{ direction.x > 0.f ? sv.cells : -1, direction.y > 0.f ? sv.cells : -1, direction.z > 0.f ? sv.cells_height : -1 };
+	const I3 lim{ sv.cells, sv.cells, sv.cells_height };
 
 	int step_axis = -1;
 	for (;;) {
+		// Is the cell possibly non-empty? Shared-memory bitmap over blocks of cells first, then one bit per cell (global).
 		bool maybe = true;
 		if (COUNT) wc->steps++;
 		if (coarse_smem) {
 			const int cb = (a.pos.x >> sv.coarse_shift) + (a.pos.y >> sv.coarse_shift) * sv.coarse_nx + (a.pos.z >> sv.coarse_shift) * sv.coarse_nxy;
 			maybe = (coarse_smem[cb >> 5] >> (cb & 31)) & 1u;
+			if (maybe) {
+				const int fb = (a.pos.x >> 2) + (a.pos.y >> 2) * sv.fine_nx + (a.pos.z >> 2) * sv.fine_nxy;
+				const int bit = (a.pos.x & 3) | ((a.pos.y & 3) << 2) | ((a.pos.z & 3) << 4);
+				maybe = (__ldg(sv.fine + (size_t)fb * 2 + (bit >> 5)) >> (bit & 31)) & 1u;
+			}
 		}
 		if (maybe) {
 			const int sc = (a.pos.x >> 4) + (a.pos.y >> 4) * sv.supergrid_xy + (a.pos.z >> 4) * sv.supergrid_xy * sv.supergrid_xy;  // voxel.cuh:197
@@ -270,7 +297,7 @@ __device__ __forceinline__ bool intersect_voxel(const SceneView& sv, const uint3
 			if (index) {
 				float new_distance = 0.f;
 				if (step_axis != -1) {
-					normal = F3{ step_axis == 0 ? -a.step.x : 0.f, step_axis == 1 ? -a.step.y : 0.f, step_axis == 2 ? -a.step.z : 0.f };
+					normal = axis_normal(a, step_axis);
 					new_distance = comp(a.tmax, step_axis) - comp(a.tdelta, step_axis);
 				}
 				const int dx = cam.x - a.pos.x, dy = cam.y - a.pos.y, dz = cam.z - a.pos.z;
@@ -313,7 +340,7 @@ __device__ __forceinline__ bool intersect_voxel(const SceneView& sv, const uint3
 				}
 			}
 		}
-		if (!dda_advance(a, out, step_axis)) break;
+		if (!dda_advance(a, lim, step_axis)) break;
 	}
 	return false;
 }

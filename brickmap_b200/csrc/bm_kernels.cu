@@ -1,25 +1,30 @@
 // Kernels and C ABI of the B200 path tracer (include/brickmap_b200.h).
 //
 // Execution model (B200-first, not the reference's five atomically-fed wavefront kernels, kernel.cu:412-420):
-//   * ONE persistent kernel per frame (frame_kernel). A thread owns one of the frame's N segment slots from ray
-//     generation (or survivor fetch) through extend, shade and its shadow ray, with the path vertex in registers;
-//     the 64-byte RayQueue record is touched once on the way in (survivors only) and once on the way out
-//     (survivors only), as four 128-bit transactions. The reference moves ~310 B per slot through HBM/L2.
-//   * Slots are handed out in tiles of 256 by one atomic per tile (the reference: one same-address atomic per
-//     ray per kernel, kernel.cu:158,228,245,330). Survivors of a tile are compacted in slot order with
-//     __ballot_sync/__popc + a shared-memory warp scan and written tile-locally; a 1-block scan kernel turns the
-//     tile counts into the next frame's slot numbering, advances the pixel cursor and the frame counter on the
-//     device (set_wavefront_globals, kernel.cu:122-139) -- no host round trip between frames.
-//   * The emptiness bitmap of the cell grid (1 bit per 4x4x4 cells at reference dims = 32 KiB) lives in shared
-//     memory; the DDA performs the reference's exact float step sequence but only loads an index word where the
-//     bitmap says the block is not empty. Index words of a flat arena are addressed directly (no pointer-table
-//     dependent load, voxel.cuh:197-198).
-//   * Slot order == "the reference scheduled one thread at a time", so seeds (kernel.cu:165,252) and results
-//     are reproducible and comparable with the reference launched <<<1,1>>>.
+//   * ONE kernel per frame (frame_kernel). A thread owns one of the frame's N segment slots from ray generation (or
+//     survivor fetch) through extend, shade and its shadow ray, with the path vertex in registers; the 64-byte RayQueue
+//     record is touched once on the way in (survivors only) and once on the way out (survivors only), as four 128-bit
+//     transactions; shadow rays never leave registers. The reference moves ~310 B per slot through L2/HBM.
+//   * Warps pull runs of 128 consecutive slots with one atomic per run (the reference: one same-address atomic per ray per
+//     kernel, kernel.cu:158,228,245,330). Survivors are written sparse at their slot and flagged in a bitmask with one
+//     __ballot_sync per warp; a 1-block scan kernel turns the mask popcounts into the next frame's slot numbering (search +
+//     select in survivor_ptr), advances the pixel cursor and the frame counter on the device (set_wavefront_globals,
+//     kernel.cu:122-139). No block barrier inside a frame, no host round trip between frames.
+//   * Two derived emptiness bitmaps: 1 bit per 4x4x4 cells in shared memory (32 KiB at reference dims, one LDS per DDA
+//     step) and 1 bit per cell in global memory (2 MiB, touched only inside non-empty blocks). The DDA performs the
+//     reference's exact float step sequence (hand-scheduled in PTX, 21 SASS instructions per step) but loads an index word
+//     only for cells that are really non-empty (2.2 per ray instead of the reference's 88). Index words of a flat arena are
+//     addressed directly (no pointer-table dependent load, voxel.cuh:197-198).
+//   * 64 registers per thread -> 4 blocks of 256 threads per SM.
+//   * Slot order == "the reference scheduled one thread at a time", so seeds (kernel.cu:165,252) and results are
+//     reproducible and comparable with the reference launched <<<1,1>>>.
+// A warp-level state-machine variant (lane refill, deferred shading, exact multi-step jumps through empty blocks) was built
+// and measured; it produced identical results but did not beat this kernel (profiles/README.md, profiles/experiments/).
 #include <cuda_runtime.h>
 
 #include <cmath>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <new>
 #include <vector>
@@ -44,14 +49,18 @@ struct DeviceState {
 
 struct FrameIO {
 	DeviceState* st;
-	const bm_ray* in;           // survivors of the previous frame: dense [0,c) when in_prefix == nullptr, else tile-local
-	const uint32_t* in_prefix;  // exclusive prefix of the previous frame's tile counts (ntiles + 1 entries)
-	bm_ray* out;                // survivors of this frame, tile-local (tile t at out + t * kTile)
-	uint32_t* out_count;        // per tile
-	bm_ray* record;             // RECORD: the reference's work queue, post-extend record of every slot
-	bm_shadow* shadow_out;      // RECORD: shadow rays, tile-local
-	uint32_t* shadow_count;     // RECORD: per tile
-	float4* accum;              // blit_buffer (state.h:22)
+	// survivors of the previous frame. in_prefix == nullptr: dense records [0,c) (a caller's queue). Otherwise SPARSE: the
+	// survivor that came out of slot s of the previous frame sits at in[s], bit s of in_mask is set, and in_prefix[t] counts
+	// the survivors of slots < 256 t, so that survivor number k (= this frame's slot k) is found by search + select.
+	const bm_ray* in;
+	const uint32_t* in_mask;
+	const uint32_t* in_prefix;
+	bm_ray* out;             // survivors of this frame, sparse by slot
+	uint32_t* out_mask;      // 1 bit per slot (zero on entry)
+	bm_ray* record;          // RECORD: the reference's work queue, post-extend record of every slot
+	bm_shadow* shadow_out;   // RECORD: shadow rays, sparse by slot
+	uint32_t* shadow_mask;   // RECORD
+	float4* accum;           // blit_buffer (state.h:22)
 	uint32_t ntiles;
 };
 
@@ -60,23 +69,29 @@ __device__ __forceinline__ void accum_add(float4* accum, uint32_t pixel, float r
 	atomicAdd(accum + pixel, make_float4(r, g, b, a));
 }
 
-// exclusive rank of `flag` among the block's threads in thread order; *total = block count
-__device__ __forceinline__ uint32_t block_rank(bool flag, uint32_t* s_warp, uint32_t* total) {
-	const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-	const uint32_t ballot = __ballot_sync(0xFFFFFFFFu, flag);
-	const uint32_t within = __popc(ballot & ((1u << lane) - 1u));
-	if (lane == 0) s_warp[warp] = __popc(ballot);
-	__syncthreads();
-	uint32_t base = 0, sum = 0;
+// Where is survivor number `k` of the previous frame? Stable compaction = the reference's atomicAdd(&primary_ray_cnt, 1)
+// (kernel.cu:298-299) with the schedule fixed to slot order; the records themselves are never moved.
+__device__ __forceinline__ const bm_ray* survivor_ptr(const FrameIO& io, uint32_t k) {
+	if (!io.in_prefix) return io.in + k;
+	uint32_t lo = 0, hi = io.ntiles;  // tile t = max{ t : prefix[t] <= k }
+	while (hi - lo > 1) {
+		const uint32_t mid = (lo + hi) >> 1;
+		if (__ldg(io.in_prefix + mid) <= k) lo = mid; else hi = mid;
+	}
+	uint32_t r = k - __ldg(io.in_prefix + lo);
+	const uint32_t* m = io.in_mask + (size_t)lo * (kTile / 32);
+	uint32_t pos = 0;
 #pragma unroll
 	for (int w = 0; w < kTile / 32; w++) {
-		const uint32_t v = s_warp[w];
-		if (w < (int)warp) base += v;
-		sum += v;
+		const uint32_t word = __ldg(m + w);
+		const uint32_t cnt = __popc(word);
+		if (r < cnt) {
+			pos = w * 32 + __fns(word, 0, r + 1);
+			break;
+		}
+		r -= cnt;
 	}
-	__syncthreads();
-	*total = sum;
-	return base + within;
+	return io.in + (size_t)lo * kTile + pos;
 }
 
 __device__ __forceinline__ unsigned long long warp_sum(unsigned long long v) {
@@ -85,13 +100,19 @@ __device__ __forceinline__ unsigned long long warp_sum(unsigned long long v) {
 	return v;
 }
 
-template <bool RECORD, bool COUNT>
-__global__ void __launch_bounds__(kTile) frame_kernel(const FrameParams fp, const SceneView sv, const FrameIO io) {
-	extern __shared__ uint32_t s_coarse[];
-	__shared__ uint32_t s_tile;
-	__shared__ uint32_t s_warp[kTile / 32];
-	__shared__ unsigned long long s_stats[8];
+__device__ __forceinline__ void store_shadow(bm_shadow* q, const F3& o, const F3& d, const F3& c, uint32_t pixel) {  // kernel.cu:277-278
+	q->origin[0] = o.x; q->origin[1] = o.y; q->origin[2] = o.z;
+	q->direction[0] = d.x; q->direction[1] = d.y; q->direction[2] = d.z;
+	q->color[0] = c.x; q->color[1] = c.y; q->color[2] = c.z;
+	q->pixel_index = pixel;
+}
 
+// ---- the frame kernel: one thread owns one slot from ray generation / survivor fetch through extend, shade and its shadow
+// ray. RECORD (bm_launch_frame) additionally leaves every buffer the reference's five kernels leave; COUNT fills the work
+// counters. Warps pull runs of 128 consecutive slots; there is no block-level synchronisation inside a frame.
+template <bool RECORD, bool COUNT>
+__global__ void __launch_bounds__(kTile, 4) frame_kernel(const FrameParams fp, const SceneView sv, const FrameIO io) {
+	extern __shared__ uint32_t s_coarse[];
 	DeviceState* st = io.st;
 	if (st->done) return;
 	const uint32_t* coarse = nullptr;
@@ -99,7 +120,6 @@ __global__ void __launch_bounds__(kTile) frame_kernel(const FrameParams fp, cons
 		for (uint32_t i = threadIdx.x; i < sv.coarse_words; i += blockDim.x) s_coarse[i] = __ldg(sv.coarse + i);
 		coarse = s_coarse;
 	}
-	if (threadIdx.x < 8) s_stats[threadIdx.x] = 0;
 	__syncthreads();
 
 	const uint32_t c = st->primary_ray_cnt;
@@ -108,32 +128,29 @@ __global__ void __launch_bounds__(kTile) frame_kernel(const FrameParams fp, cons
 	unsigned long long n_shadow = 0, n_term = 0, n_unocc = 0;
 	WorkCounters wc{ 0, 0, 0, 0 };
 
+	// each warp pulls runs of kRun * 32 consecutive slots with one atomic (the reference: one same-address atomic per ray per
+	// kernel, kernel.cu:158,228,245,330); no block-level synchronisation inside the frame
+	constexpr uint32_t kRun = 4;
+	const uint32_t lane = threadIdx.x & 31;
+	const uint32_t nruns = (fp.n_slots + kRun * 32 - 1) / (kRun * 32);
+	uint32_t run = 0, round = kRun;
 	for (;;) {
-		if (threadIdx.x == 0) s_tile = atomicAdd(&st->tile_ticket, 1u);
-		__syncthreads();
-		const uint32_t tile = s_tile;
-		if (tile >= io.ntiles) break;
-		const uint32_t slot = tile * kTile + threadIdx.x;
+		if (round == kRun) {
+			if (lane == 0) run = atomicAdd(&st->tile_ticket, 1u);
+			run = __shfl_sync(0xFFFFFFFFu, run, 0);
+			if (run >= nruns) break;
+			round = 0;
+		}
+		const uint32_t slot = (run * kRun + round) * 32 + lane;
+		round++;
+		if (slot - lane >= fp.n_slots) continue;
 		const bool valid = slot < fp.n_slots;
 		Ray ray;
 		bool survives = false, has_shadow = false;
 		F3 shadow_dir{ 0, 0, 0 }, shadow_color{ 0, 0, 0 };
 		if (valid) {
-			if (slot < c) {
-				const bm_ray* src = io.in + slot;
-				if (io.in_prefix) {
-					// survivor `slot` of the previous frame lives in source tile t = max{ t : prefix[t] <= slot }
-					uint32_t lo = 0, hi = io.ntiles;
-					while (hi - lo > 1) {
-						const uint32_t mid = (lo + hi) >> 1;
-						if (__ldg(io.in_prefix + mid) <= slot) lo = mid; else hi = mid;
-					}
-					src = io.in + (size_t)lo * kTile + (slot - __ldg(io.in_prefix + lo));
-				}
-				ray = load_ray(src);
-			} else {
-				ray = generate_primary(fp, frame, start, slot - c);  // primary_rays, kernel.cu:154-223
-			}
+			if (slot < c) ray = load_ray(survivor_ptr(io, slot));
+			else ray = generate_primary(fp, frame, start, slot - c);  // primary_rays, kernel.cu:154-223
 			// extend, kernel.cu:226-238
 			ray.distance = kVeryFar;
 			intersect_voxel<COUNT>(sv, coarse, ray.origin, ray.direction, ray.normal, ray.distance, fp.cam_cell, &wc);
@@ -158,73 +175,55 @@ __global__ void __launch_bounds__(kTile) frame_kernel(const FrameParams fp, cons
 				}
 			}
 		}
-		// stable (slot-ordered) compaction of the survivors: the reference's atomicAdd(&primary_ray_cnt,1)
-		// (kernel.cu:298-299) with the schedule fixed to slot order
-		uint32_t total;
-		const uint32_t rank = block_rank(survives, s_warp, &total);
-		if (survives) store_ray(io.out + (size_t)tile * kTile + rank, ray);
-		if (threadIdx.x == 0) io.out_count[tile] = total;
+		if (survives) store_ray(io.out + slot, ray);
+		const uint32_t smask = __ballot_sync(0xFFFFFFFFu, survives);
+		if (lane == 0) io.out_mask[slot >> 5] = smask;
 		if (RECORD) {
-			uint32_t stotal;
-			const uint32_t srank = block_rank(has_shadow, s_warp, &stotal);
-			if (has_shadow) {
-				bm_shadow* q = io.shadow_out + (size_t)tile * kTile + srank;  // kernel.cu:277-278
-				q->origin[0] = ray.origin.x; q->origin[1] = ray.origin.y; q->origin[2] = ray.origin.z;
-				q->direction[0] = shadow_dir.x; q->direction[1] = shadow_dir.y; q->direction[2] = shadow_dir.z;
-				q->color[0] = shadow_color.x; q->color[1] = shadow_color.y; q->color[2] = shadow_color.z;
-				q->pixel_index = ray.pixel_index;
-			}
-			if (threadIdx.x == 0) io.shadow_count[tile] = stotal;
+			if (has_shadow) store_shadow(io.shadow_out + slot, ray.origin, shadow_dir, shadow_color, ray.pixel_index);
+			const uint32_t hmask = __ballot_sync(0xFFFFFFFFu, has_shadow);
+			if (lane == 0) io.shadow_mask[slot >> 5] = hmask;
 		}
 	}
 
-	// per-block statistics -> a handful of atomics per block
+	// per-warp statistics -> a handful of atomics per warp
 	n_shadow = warp_sum(n_shadow);
 	n_term = warp_sum(n_term);
 	n_unocc = warp_sum(n_unocc);
-	if ((threadIdx.x & 31) == 0) {
-		atomicAdd(&s_stats[0], n_shadow);
-		atomicAdd(&s_stats[1], n_term);
-		atomicAdd(&s_stats[2], n_unocc);
+	if (lane == 0) {
+		if (n_shadow) atomicAdd(&st->shadow_rays, n_shadow);
+		if (n_term) atomicAdd(&st->terminations, n_term);
+		if (n_term) atomicAdd(&st->paths_since_reset, n_term);
+		if (n_unocc) atomicAdd(&st->unoccluded, n_unocc);
 	}
 	if (COUNT) {
 		const unsigned long long a = warp_sum(wc.index_reads), b = warp_sum(wc.bricks), q = warp_sum(wc.requests), t = warp_sum(wc.steps);
-		if ((threadIdx.x & 31) == 0) {
-			atomicAdd(&s_stats[3], a);
-			atomicAdd(&s_stats[4], b);
-			atomicAdd(&s_stats[5], q);
-			atomicAdd(&s_stats[6], t);
-		}
-	}
-	__syncthreads();
-	if (threadIdx.x == 0) {
-		if (s_stats[0]) atomicAdd(&st->shadow_rays, s_stats[0]);
-		if (s_stats[1]) atomicAdd(&st->terminations, s_stats[1]);
-		if (s_stats[1]) atomicAdd(&st->paths_since_reset, s_stats[1]);
-		if (s_stats[2]) atomicAdd(&st->unoccluded, s_stats[2]);
-		if (COUNT) {
-			atomicAdd(&st->index_reads, s_stats[3]);
-			atomicAdd(&st->bricks, s_stats[4]);
-			atomicAdd(&st->requests, s_stats[5]);
-			atomicAdd(&st->cell_steps, s_stats[6]);
+		if (lane == 0) {
+			atomicAdd(&st->index_reads, a);
+			atomicAdd(&st->bricks, b);
+			atomicAdd(&st->requests, q);
+			atomicAdd(&st->cell_steps, t);
 		}
 	}
 }
 
-// set_wavefront_globals (kernel.cu:122-139) + exclusive scan of the tile counts. One block.
-// counts[ntiles] -> prefix[ntiles + 1]; optional second pair for the shadow queue (RECORD).
-__global__ void __launch_bounds__(1024) scan_kernel(DeviceState* st, const uint32_t* counts, uint32_t* prefix, const uint32_t* shadow_counts,
-                                                     uint32_t* shadow_prefix, uint32_t ntiles, uint32_t n_slots, uint32_t pixels) {
+// set_wavefront_globals (kernel.cu:122-139) + per-tile survivor counts (popcount of the slot masks) -> exclusive prefix.
+// One block. mask[ntiles * 8] -> prefix[ntiles + 1]; optional second pair for the shadow queue (RECORD). Also zeroes
+// `clear_mask`, the mask buffer the NEXT frame will write with atomicOr.
+__global__ void __launch_bounds__(1024) scan_kernel(DeviceState* st, const uint32_t* mask, uint32_t* prefix, const uint32_t* shadow_mask, uint32_t* shadow_prefix,
+                                                     uint32_t* clear_mask, uint32_t ntiles, uint32_t n_slots, uint32_t pixels) {
 	__shared__ uint32_t s_part[1024];
 	if (st->done) return;
 	const uint32_t per = (ntiles + blockDim.x - 1) / blockDim.x;
 	for (int pass = 0; pass < 2; pass++) {
-		const uint32_t* in = pass == 0 ? counts : shadow_counts;
+		const uint32_t* in = pass == 0 ? mask : shadow_mask;
 		uint32_t* out = pass == 0 ? prefix : shadow_prefix;
 		if (!in) continue;
 		const uint32_t b = min(ntiles, threadIdx.x * per), e = min(ntiles, b + per);
 		uint32_t sum = 0;
-		for (uint32_t i = b; i < e; i++) sum += in[i];
+		for (uint32_t i = b; i < e; i++) {
+			const uint4 lo = *reinterpret_cast<const uint4*>(in + (size_t)i * 8), hi = *reinterpret_cast<const uint4*>(in + (size_t)i * 8 + 4);
+			sum += __popc(lo.x) + __popc(lo.y) + __popc(lo.z) + __popc(lo.w) + __popc(hi.x) + __popc(hi.y) + __popc(hi.z) + __popc(hi.w);
+		}
 		s_part[threadIdx.x] = sum;
 		__syncthreads();
 		for (uint32_t off = 1; off < blockDim.x; off <<= 1) {  // Hillis-Steele inclusive scan of the partials
@@ -236,7 +235,8 @@ __global__ void __launch_bounds__(1024) scan_kernel(DeviceState* st, const uint3
 		uint32_t run = s_part[threadIdx.x] - sum;
 		for (uint32_t i = b; i < e; i++) {
 			out[i] = run;
-			run += in[i];
+			const uint4 lo = *reinterpret_cast<const uint4*>(in + (size_t)i * 8), hi = *reinterpret_cast<const uint4*>(in + (size_t)i * 8 + 4);
+			run += __popc(lo.x) + __popc(lo.y) + __popc(lo.z) + __popc(lo.w) + __popc(hi.x) + __popc(hi.y) + __popc(hi.z) + __popc(hi.w);
 		}
 		const uint32_t total = s_part[blockDim.x - 1];
 		__syncthreads();
@@ -257,6 +257,8 @@ __global__ void __launch_bounds__(1024) scan_kernel(DeviceState* st, const uint3
 		}
 		__syncthreads();
 	}
+	if (clear_mask)
+		for (uint32_t i = threadIdx.x; i < ntiles * 2; i += blockDim.x) reinterpret_cast<uint4*>(clear_mask)[i] = make_uint4(0, 0, 0, 0);
 }
 
 // start of a bm_render / bm_launch_frame call: install the stop target; a target that is already met stops at once
@@ -266,13 +268,29 @@ __global__ void begin_kernel(DeviceState* st, unsigned long long target_paths) {
 	st->tile_ticket = 0;
 }
 
-// tile-local -> dense (the layout the reference's queues have): dst[prefix[t] + j] = src[t * kTile + j]
+// sparse-by-slot -> dense (the layout the reference's queues have): dst[prefix[t] + rank of slot within tile t] = src[slot]
 template <typename T>
-__global__ void __launch_bounds__(kTile) export_kernel(const T* src, const uint32_t* prefix, T* dst, uint32_t ntiles) {
+__global__ void __launch_bounds__(kTile) export_kernel(const T* src, const uint32_t* mask, const uint32_t* prefix, T* dst, uint32_t ntiles) {
 	const uint32_t tile = blockIdx.x;
 	if (tile >= ntiles) return;
-	const uint32_t base = prefix[tile], n = prefix[tile + 1] - base;
-	if (threadIdx.x < n) dst[base + threadIdx.x] = src[(size_t)tile * kTile + threadIdx.x];
+	const uint32_t* m = mask + (size_t)tile * (kTile / 32);
+	const uint32_t w = threadIdx.x >> 5, lane = threadIdx.x & 31;
+	const uint32_t word = m[w];
+	if (!((word >> lane) & 1u)) return;
+	uint32_t rank = __popc(word & ((1u << lane) - 1u));
+	for (uint32_t k = 0; k < w; k++) rank += __popc(m[k]);
+	dst[prefix[tile] + rank] = src[(size_t)tile * kTile + threadIdx.x];
+}
+
+
+// dense survivor set -> the private sparse representation: slots [0, count) all present
+__global__ void import_masks_kernel(uint32_t* mask, uint32_t* prefix, uint32_t ntiles, uint32_t count) {
+	const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+	if (i < ntiles * 8) {
+		const uint32_t first = i * 32;
+		mask[i] = count >= first + 32 ? 0xFFFFFFFFu : (count > first ? ((1u << (count - first)) - 1u) : 0u);
+	}
+	if (i <= ntiles) prefix[i] = min(i * (uint32_t)kTile, count);
 }
 
 // upload, kernel.cu:141-151, with the count read on the device (the reference copies it to the host first,
@@ -385,6 +403,28 @@ __global__ void coarse_build_kernel(const SceneView sv, uint32_t* coarse, uint32
 	if ((threadIdx.x & 31) == 0 && (b >> 5) < sv.coarse_words) coarse[b >> 5] = ballot;
 }
 
+// per-cell emptiness, 64 bits per 4x4x4 block of cells
+__global__ void fine_build_kernel(const SceneView sv, uint32_t* fine, uint32_t nblocks) {
+	const uint32_t b = blockIdx.x * blockDim.x + threadIdx.x;
+	if (b >= nblocks) return;
+	const int bx = b % sv.fine_nx, by = (b / sv.fine_nx) % (sv.fine_nxy / sv.fine_nx), bz = b / sv.fine_nxy;
+	uint32_t lo = 0, hi = 0;
+	for (int z = 0; z < 4; z++)
+		for (int y = 0; y < 4; y++)
+			for (int x = 0; x < 4; x++) {
+				const int px = bx * 4 + x, py = by * 4 + y, pz = bz * 4 + z;
+				if (px >= sv.cells || py >= sv.cells || pz >= sv.cells_height) continue;
+				const int sc = (px >> 4) + (py >> 4) * sv.supergrid_xy + (pz >> 4) * sv.supergrid_xy * sv.supergrid_xy;
+				const int local = (px & 15) + (py & 15) * 16 + (pz & 15) * 256;
+				if (sv.indices[sc][local]) {
+					const int bit = x | (y << 2) | (z << 4);
+					if (bit < 32) lo |= 1u << bit; else hi |= 1u << (bit - 32);
+				}
+			}
+	fine[(size_t)b * 2] = lo;
+	fine[(size_t)b * 2 + 1] = hi;
+}
+
 // is indices[sc] == indices[0] + sc * 4096 for every superchunk?
 __global__ void flat_check_kernel(uint32_t* const* indices, uint32_t n, uint32_t* not_flat) {
 	const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
@@ -455,10 +495,10 @@ struct bm_context {
 	DeviceState* d_state = nullptr;
 	// private survivor buffers (tile-local layout), tile counts and prefixes, double-buffered
 	bm_ray* d_rays[2] = { nullptr, nullptr };
-	uint32_t* d_count[2] = { nullptr, nullptr };
-	uint32_t* d_prefix[2] = { nullptr, nullptr };
-	bm_shadow* d_shadow = nullptr;  // RECORD scratch
-	uint32_t* d_shadow_count = nullptr;
+	uint32_t* d_mask[2] = { nullptr, nullptr };    // 1 bit per slot: survivor present
+	uint32_t* d_prefix[2] = { nullptr, nullptr };  // survivors before each 256-slot tile
+	bm_shadow* d_shadow = nullptr;  // RECORD scratch (sparse by slot)
+	uint32_t* d_shadow_mask = nullptr;
 	uint32_t* d_shadow_prefix = nullptr;
 	int cur = 0;                 // which private buffer holds the survivors of the last frame
 	bool private_valid = false;  // survivors of the last frame are in d_rays[cur] (tile-local)
@@ -467,6 +507,7 @@ struct bm_context {
 	bm_gpu_scene scene{};
 	SceneView sv{};
 	uint32_t* d_coarse = nullptr;
+	uint32_t* d_fine = nullptr;
 	uint32_t* d_flag = nullptr;
 	// host statics of launch_kernels (kernel.cu:367-382)
 	bm_camera cam{};
@@ -564,14 +605,15 @@ void bm_destroy(bm_context* c) {
 	cudaSetDevice(c->cfg.device);
 	for (int i = 0; i < 2; i++) {
 		cudaFree(c->d_rays[i]);
-		cudaFree(c->d_count[i]);
+		cudaFree(c->d_mask[i]);
 		cudaFree(c->d_prefix[i]);
 	}
 	cudaFree(c->d_shadow);
-	cudaFree(c->d_shadow_count);
+	cudaFree(c->d_shadow_mask);
 	cudaFree(c->d_shadow_prefix);
 	cudaFree(c->d_state);
 	cudaFree(c->d_coarse);
+	cudaFree(c->d_fine);
 	cudaFree(c->d_flag);
 	for (cudaEvent_t e : c->events) cudaEventDestroy(e);
 	if (c->stream) cudaStreamDestroy(c->stream);
@@ -609,12 +651,13 @@ int bm_create(bm_context** out, const bm_config* cfg) {
 	CKC(cudaMemcpy(&c->d_state->frame, &one, 4, cudaMemcpyHostToDevice));
 	for (int i = 0; i < 2; i++) {
 		CKC(cudaMalloc(&c->d_rays[i], (size_t)c->ntiles * kTile * sizeof(bm_ray)));
-		CKC(cudaMalloc(&c->d_count[i], (size_t)c->ntiles * 4));
+		CKC(cudaMalloc(&c->d_mask[i], (size_t)c->ntiles * 32));
 		CKC(cudaMalloc(&c->d_prefix[i], (size_t)(c->ntiles + 1) * 4));
-		CKC(cudaMemset(c->d_count[i], 0, (size_t)c->ntiles * 4));
+		CKC(cudaMemset(c->d_mask[i], 0, (size_t)c->ntiles * 32));
 		CKC(cudaMemset(c->d_prefix[i], 0, (size_t)(c->ntiles + 1) * 4));
 	}
-	CKC(cudaMalloc(&c->d_shadow_count, (size_t)c->ntiles * 4));
+	CKC(cudaMalloc(&c->d_shadow_mask, (size_t)c->ntiles * 32));
+	CKC(cudaMemset(c->d_shadow_mask, 0, (size_t)c->ntiles * 32));
 	CKC(cudaMalloc(&c->d_shadow_prefix, (size_t)(c->ntiles + 1) * 4));
 	CKC(cudaMalloc(&c->d_flag, 4));
 #undef CKC
@@ -666,6 +709,16 @@ int bm_scene_bind(bm_context* c, bm_gpu_scene scene) {
 	const uint32_t nblocks = (uint32_t)bits;
 	coarse_build_kernel<<<(sv.coarse_words * 32 + 255) / 256, 256, 0, c->stream>>>(sv, c->d_coarse, nblocks);
 	CK(cudaGetLastError());
+	sv.fine = nullptr;
+	sv.fine_nx = (sv.cells + 3) >> 2;
+	sv.fine_nxy = sv.fine_nx * sv.fine_nx;
+	const uint32_t nfine = (uint32_t)sv.fine_nxy * (uint32_t)((sv.cells_height + 3) >> 2);
+	cudaFree(c->d_fine);
+	c->d_fine = nullptr;
+	CK(cudaMalloc(&c->d_fine, (size_t)nfine * 8));
+	fine_build_kernel<<<(nfine + 255) / 256, 256, 0, c->stream>>>(sv, c->d_fine, nfine);
+	CK(cudaGetLastError());
+	c->launches += 1;
 	const uint32_t nsc = (uint32_t)(sv.supergrid_xy * sv.supergrid_xy * (sv.cells_height / 16));
 	CK(cudaMemsetAsync(c->d_flag, 0, 4, c->stream));
 	flat_check_kernel<<<(nsc + 255) / 256, 256, 0, c->stream>>>(scene.indices, nsc, c->d_flag);
@@ -677,6 +730,7 @@ int bm_scene_bind(bm_context* c, bm_gpu_scene scene) {
 	CK(cudaMemcpyAsync(&first, scene.indices, sizeof(uint32_t*), cudaMemcpyDeviceToHost, c->stream));
 	CK(cudaStreamSynchronize(c->stream));
 	sv.coarse = c->d_coarse;
+	sv.fine = c->d_fine;
 	sv.flat_indices = not_flat ? nullptr : first;
 	// launch geometry of the persistent frame kernel
 	c->frame_smem = (size_t)sv.coarse_words * 4;
@@ -841,8 +895,9 @@ static int launch_frame_kernels(bm_context* c, const FrameIO& io, bool count) {
 	else frame_kernel<RECORD, false><<<blocks, kTile, c->frame_smem, c->stream>>>(c->fp, c->sv, io);
 	CK(cudaGetLastError());
 	if (c->timing) CK(cudaEventRecord(e1, c->stream));
-	scan_kernel<<<1, 1024, 0, c->stream>>>(c->d_state, io.out_count, c->d_prefix[c->cur ^ 1], RECORD ? io.shadow_count : nullptr,
-	                                       RECORD ? c->d_shadow_prefix : nullptr, c->ntiles, c->cfg.ray_queue_buffer_size, c->tile_pixels);
+	// the mask that was this frame's input becomes the next frame's output: the scan clears it
+	scan_kernel<<<1, 1024, 0, c->stream>>>(c->d_state, io.out_mask, c->d_prefix[c->cur ^ 1], RECORD ? io.shadow_mask : nullptr,
+	                                       RECORD ? c->d_shadow_prefix : nullptr, c->d_mask[c->cur], c->ntiles, c->cfg.ray_queue_buffer_size, c->tile_pixels);
 	CK(cudaGetLastError());
 	c->launches += 2;
 	return 0;
@@ -870,24 +925,26 @@ int bm_launch_frame(bm_context* c, float* blit, bm_ray* queue, bm_ray* queue2, b
 		// survivors of the previous frame are still in the private tile-local buffer; the caller's swapped `queue`
 		// holds the same records densely (main.cpp:146) and is not needed
 		io.in = c->d_rays[c->cur];
+		io.in_mask = c->d_mask[c->cur];
 		io.in_prefix = c->d_prefix[c->cur];
 	} else {
 		io.in = queue;  // dense survivors [0, primary_ray_cnt) supplied by the caller (after bm_set_counters)
+		io.in_mask = nullptr;
 		io.in_prefix = nullptr;
 	}
 	io.out = c->d_rays[c->cur ^ 1];
-	io.out_count = c->d_count[c->cur ^ 1];
+	io.out_mask = c->d_mask[c->cur ^ 1];
 	io.record = queue;
 	io.shadow_out = c->d_shadow;
-	io.shadow_count = c->d_shadow_count;
+	io.shadow_mask = c->d_shadow_mask;
 	io.accum = reinterpret_cast<float4*>(blit);
 	io.ntiles = c->ntiles;
 	rc = launch_frame_kernels<true>(c, io, (flags & BM_FRAME_COUNT_WORK) != 0);
 	if (rc) return rc;
 	c->cur ^= 1;
-	export_kernel<bm_ray><<<c->ntiles, kTile, 0, c->stream>>>(c->d_rays[c->cur], c->d_prefix[c->cur], queue2, c->ntiles);
+	export_kernel<bm_ray><<<c->ntiles, kTile, 0, c->stream>>>(c->d_rays[c->cur], c->d_mask[c->cur], c->d_prefix[c->cur], queue2, c->ntiles);
 	CK(cudaGetLastError());
-	export_kernel<bm_shadow><<<c->ntiles, kTile, 0, c->stream>>>(c->d_shadow, c->d_shadow_prefix, shadow_queue, c->ntiles);
+	export_kernel<bm_shadow><<<c->ntiles, kTile, 0, c->stream>>>(c->d_shadow, c->d_shadow_mask, c->d_shadow_prefix, shadow_queue, c->ntiles);
 	CK(cudaGetLastError());
 	c->launches += 2;
 	c->private_valid = true;
@@ -908,6 +965,8 @@ int bm_render(bm_context* c, float* blit, uint32_t frames, uint64_t target_paths
 		// no private survivor set (first frame, or the counters were set by the caller): start from an empty one
 		CK(cudaMemsetAsync(&c->d_state->primary_ray_cnt, 0, 4, c->stream));
 		CK(cudaMemsetAsync(c->d_prefix[c->cur], 0, (size_t)(c->ntiles + 1) * 4, c->stream));
+		CK(cudaMemsetAsync(c->d_mask[c->cur], 0, (size_t)c->ntiles * 32, c->stream));
+		CK(cudaMemsetAsync(c->d_mask[c->cur ^ 1], 0, (size_t)c->ntiles * 32, c->stream));
 		c->private_valid = true;
 	}
 	for (uint32_t f = 0; f < frames; f++) {
@@ -918,9 +977,10 @@ int bm_render(bm_context* c, float* blit, uint32_t frames, uint64_t target_paths
 		FrameIO io{};
 		io.st = c->d_state;
 		io.in = c->d_rays[c->cur];
+		io.in_mask = c->d_mask[c->cur];
 		io.in_prefix = c->d_prefix[c->cur];
 		io.out = c->d_rays[c->cur ^ 1];
-		io.out_count = c->d_count[c->cur ^ 1];
+		io.out_mask = c->d_mask[c->cur ^ 1];
 		io.accum = reinterpret_cast<float4*>(blit);
 		io.ntiles = c->ntiles;
 		rc = launch_frame_kernels<false>(c, io, (flags & BM_FRAME_COUNT_WORK) != 0);
@@ -928,6 +988,30 @@ int bm_render(bm_context* c, float* blit, uint32_t frames, uint64_t target_paths
 		c->cur ^= 1;
 	}
 	if (sync) CK(cudaStreamSynchronize(c->stream));
+	return 0;
+}
+
+int bm_import_rays(bm_context* c, const bm_ray* queue, uint32_t count) {
+	if (!c || (count && !queue) || count > c->cfg.ray_queue_buffer_size) return fail_api(BM_E_INVALID, "bm_import_rays: bad argument");
+	CK(cudaSetDevice(c->cfg.device));
+	if (count) CK(cudaMemcpyAsync(c->d_rays[c->cur], queue, (size_t)count * sizeof(bm_ray), cudaMemcpyDeviceToDevice, c->stream));
+	import_masks_kernel<<<(c->ntiles * 8 + 256) / 256, 256, 0, c->stream>>>(c->d_mask[c->cur], c->d_prefix[c->cur], c->ntiles, count);
+	CK(cudaGetLastError());
+	CK(cudaMemsetAsync(c->d_mask[c->cur ^ 1], 0, (size_t)c->ntiles * 32, c->stream));
+	CK(cudaMemcpyAsync(&c->d_state->primary_ray_cnt, &c->d_prefix[c->cur][c->ntiles], 4, cudaMemcpyDeviceToDevice, c->stream));
+	c->launches += 1;
+	c->private_valid = true;
+	return 0;
+}
+
+int bm_export_rays(bm_context* c, bm_ray* queue2) {
+	if (!c || !queue2) return fail_api(BM_E_INVALID, "bm_export_rays: null argument");
+	if (!c->private_valid) return fail_api(BM_E_STATE, "bm_export_rays: no private survivor set");
+	CK(cudaSetDevice(c->cfg.device));
+	export_kernel<bm_ray><<<c->ntiles, kTile, 0, c->stream>>>(c->d_rays[c->cur], c->d_mask[c->cur], c->d_prefix[c->cur], queue2, c->ntiles);
+	CK(cudaGetLastError());
+	c->launches += 1;
+	CK(cudaStreamSynchronize(c->stream));
 	return 0;
 }
 

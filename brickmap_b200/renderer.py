@@ -228,6 +228,23 @@ class Renderer:
         """Fused throughput path: `frames` frames (or until target_paths paths finished) into blit_buffer (device tensor)."""
         check(self.lib.bm_render(self.h, blit_buffer.data_ptr(), frames, target_paths, flags, 1 if sync else 0), "bm_render")
 
+    def import_rays(self, rays):
+        """Make `rays` (numpy RAY_DTYPE records) the survivor set the next render() starts from."""
+        dev = torch.device("cuda", self.cfg.device)
+        t = torch.from_numpy(np.ascontiguousarray(rays, dtype=RAY_DTYPE).view(np.float32).copy()).to(dev)
+        torch.cuda.synchronize(dev)
+        check(self.lib.bm_import_rays(self.h, t.data_ptr(), len(rays)), "bm_import_rays")
+        self.synchronize()
+
+    def export_rays(self):
+        """The current private survivor set as dense numpy records, in slot order."""
+        dev = torch.device("cuda", self.cfg.device)
+        n = self.counters().primary_ray_cnt
+        t = torch.zeros(max(n, 1) * 16, dtype=torch.float32, device=dev)
+        torch.cuda.synchronize(dev)
+        check(self.lib.bm_export_rays(self.h, t.data_ptr()), "bm_export_rays")
+        return t.cpu().numpy().view(np.uint8)[: n * RAY_DTYPE.itemsize].view(RAY_DTYPE).copy()
+
     def render_to_host(self, blit_buffer, frames, accum_host, target_paths=0, flags=FRAME_DEFAULT, request_count_host=None, request_positions_host=None):
         """render() + device->host copies into (pinned) HOST tensors: accumulation tile, request count, request positions."""
         check(self.lib.bm_render_to_host(self.h, blit_buffer.data_ptr(), frames, target_paths, flags, accum_host.data_ptr(),

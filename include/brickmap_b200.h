@@ -165,6 +165,12 @@ int bm_launch_frame(bm_context* ctx, float* blit_buffer_device, bm_ray* queue_de
  * accumulation reset (0 = no target). Asynchronous on the context's stream unless `sync` is set. */
 int bm_render(bm_context* ctx, float* blit_buffer_device, uint32_t frames, uint64_t target_paths, uint32_t flags, int sync);
 
+/* Hand the throughput path an explicit survivor set: `count` dense records (the layout bm_launch_frame leaves in queue2) become
+ * the survivors of the previous frame, primary_ray_cnt = count. bm_export_rays is the inverse: the current private survivor set,
+ * densely, in slot order (what the reference would hold in ray_buffer_next[0, primary_ray_cnt)). */
+int bm_import_rays(bm_context* ctx, const bm_ray* queue_device, uint32_t count);
+int bm_export_rays(bm_context* ctx, bm_ray* queue2_device);
+
 /* bm_render followed by device->host copies of the results into HOST buffers: accumulation tile
  * (tile pixels * 4 floats), request count and request positions (queue_size * 3 ints; may be NULL). */
 int bm_render_to_host(bm_context* ctx, float* blit_buffer_device, uint32_t frames, uint64_t target_paths, uint32_t flags,

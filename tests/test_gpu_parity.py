@@ -193,6 +193,60 @@ def test_fused_render_matches_oracle_over_many_frames(oracle, golden, stores):
     assert_records_equal(state.rays("next", c.primary_ray_cnt), oren.rays[: c.primary_ray_cnt], what="survivors after mixing both entry points")
 
 
+@pytest.mark.parametrize("variant", ["256", "256lod"])
+def test_throughput_kernel_matches_simple_kernel_on_adversarial_rays(golden, stores, variant):
+    """The throughput path (bm_import_rays -> bm_render -> bm_export_rays, private sparse survivor storage) against the
+    reference-layout path (bm_launch_frame on caller queues) on the same injected rays: exact ties between axes (diagonal and
+    axis-aligned directions from lattice origins), zero components, origins on cell / block boundaries, outside the world,
+    all bounce counts."""
+    g = golden(variant)
+    store = stores(variant)
+    cfg = store.cfg
+    n = cfg.ray_queue_buffer_size
+    rng = np.random.default_rng(11)
+    rays = np.zeros(n, bm.RAY_DTYPE)
+    gs, gh = float(cfg.grid_size), float(cfg.grid_height)
+    o = rng.uniform([-0.2 * gs, -0.2 * gs, -0.2 * gh], [1.2 * gs, 1.2 * gs, 1.5 * gh], size=(n, 3)).astype(np.float32)
+    d = rng.normal(size=(n, 3)).astype(np.float32)
+    q = n // 8
+    o[:q] = np.round(o[:q] / 32) * 32                      # block corners
+    o[q:2 * q] = np.round(o[q:2 * q] / 8) * 8 + 4          # cell centres
+    diag = np.array([[1, 1, 0], [1, 0, 1], [0, 1, 1], [1, 1, 1], [1, -1, 0], [-1, 1, 1], [2, 1, 0], [1, 2, 2], [1, 0, 0], [0, 0, -1]], np.float32)
+    d[: 2 * q] = diag[rng.integers(0, len(diag), 2 * q)] * rng.choice([-1.0, 1.0], size=(2 * q, 1)).astype(np.float32)
+    d[2 * q:3 * q, rng.integers(0, 3)] = 0.0
+    o[3 * q:4 * q] = rng.uniform([0, 0, gh * 0.6], [gs, gs, gh], size=(q, 3)).astype(np.float32)  # inside, above the terrain
+    d /= np.linalg.norm(d, axis=1, keepdims=True)
+    rays["origin"], rays["direction"] = o, d
+    rays["throughput"] = rng.uniform(0.2, 1.0, size=(n, 3)).astype(np.float32)
+    rays["normal"] = np.eye(3, dtype=np.float32)[rng.integers(0, 3, n)] * rng.choice([-1.0, 0.0, 1.0], size=(n, 1)).astype(np.float32)
+    rays["bounces"] = rng.integers(0, 4, n)
+    rays["pixel_index"] = rng.integers(0, cfg.screen_width * cfg.screen_height, n)
+    h, w = cfg.screen_height, cfg.screen_width
+
+    simple = renderer_for(g, store)
+    state = bm.State(cfg)
+    state.write_rays(rays, "work")
+    simple.set_counters(primary_ray_cnt=n, start_position=123, frame=5)
+    simple.launch_kernels(state, flags=R.FRAME_NO_RESET)
+    cs = simple.counters()
+    want = state.rays("next", cs.primary_ray_cnt)
+
+    fast = renderer_for(g, store)
+    fast.set_counters(primary_ray_cnt=n, start_position=123, frame=5)
+    fast.import_rays(rays)
+    blit = torch.zeros(h, w, 4, dtype=torch.float32, device="cuda")
+    fast.render(blit, 1, flags=R.FRAME_NO_RESET)
+    cf = fast.counters()
+    assert [cf.primary_ray_cnt, cf.start_position, cf.frame] == [cs.primary_ray_cnt, cs.start_position, cs.frame]
+    assert 0 < cf.primary_ray_cnt < n
+    assert_records_equal(fast.export_rays(), want, what="survivors, bm_render vs bm_launch_frame")
+    a, b = blit.cpu().numpy(), state.blit_buffer.cpu().numpy()
+    assert np.array_equal(a[..., 3], b[..., 3])
+    assert_close_rel(a, b, 1e-5, "accumulation, bm_render vs bm_launch_frame")
+    sf, ss = fast.stats(), simple.stats()
+    assert [sf[k] for k in ("shadow_rays", "terminations", "unoccluded")] == [ss[k] for k in ("shadow_rays", "terminations", "unoccluded")]
+
+
 def test_work_counters_match_oracle(oracle, golden, stores):
     """S (cell steps), K (bricks entered), P, V of SURVEY 8d, which feed the roofline's algorithmic bytes."""
     g = golden("256")
