@@ -13,4 +13,4 @@ device memory and for torch.distributed plumbing.
 """
 from ._lib import BrickmapError, Camera, Config, Counters, GpuScene, Stats, load  # noqa: F401
 from .renderer import (RAY_DTYPE, SHADOW_DTYPE, Renderer, SceneStore, State, default_config, make_camera,  # noqa: F401
-                       tile_rows_for_rank)
+                       strip_rows_for_rank, tile_rows_for_rank)

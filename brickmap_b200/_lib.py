@@ -10,7 +10,8 @@ LIB_PATH = os.path.join(HERE, "libbrickmap_b200.so")
 class Config(C.Structure):  # bm_config
     _fields_ = [("device", C.c_int32), ("grid_size", C.c_int32), ("grid_height", C.c_int32), ("lod_distance_2x2x2", C.c_int32),
                 ("lod_distance_8x8x8", C.c_int32), ("brick_load_queue_size", C.c_int32), ("ray_queue_buffer_size", C.c_uint32),
-                ("screen_width", C.c_uint32), ("screen_height", C.c_uint32), ("tile_row0", C.c_uint32), ("tile_rows", C.c_uint32)]
+                ("screen_width", C.c_uint32), ("screen_height", C.c_uint32), ("tile_row0", C.c_uint32), ("tile_rows", C.c_uint32),
+                ("strip_rows", C.c_uint32), ("strip_count", C.c_uint32), ("strip_index", C.c_uint32)]
 
 
 class Camera(C.Structure):  # bm_camera

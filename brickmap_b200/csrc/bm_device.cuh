@@ -90,6 +90,7 @@ struct FrameParams {
 	I3 cam_cell;        // ivec3(camera.position / 8.f) (kernel.cu:418,420)
 	uint32_t width, height;      // full image
 	uint32_t tile_row0, tile_rows;  // rows rendered by this context
+	uint32_t strip_rows, strip_count, strip_index;  // interleaved partition (strip_rows == 0: one contiguous band)
 	uint32_t n_slots;   // ray_queue_buffer_size
 	// sun / sky constants (sunsky.cu, hoisted)
 	F3 sun_dir;
@@ -434,7 +435,7 @@ __device__ __forceinline__ Ray generate_primary(const FrameParams& fp, uint32_t 
 	const uint32_t rows = fp.tile_rows;
 	const uint32_t x = (start_position + index) % fp.width;                 // kernel.cu:170
 	const uint32_t ty = ((start_position + index) / fp.width) % rows;       // kernel.cu:171 (row inside the tile)
-	const uint32_t y = ty + fp.tile_row0;
+	const uint32_t y = fp.strip_rows ? ((ty / fp.strip_rows) * fp.strip_count + fp.strip_index) * fp.strip_rows + ty % fp.strip_rows : ty + fp.tile_row0;
 	float sx, sy;
 	stratified_sample(seed, sx, sy);
 	const float px = (float)x - sx;

@@ -553,6 +553,9 @@ static void update_frame_params(bm_context* c) {
 	fp.height = c->cfg.screen_height;
 	fp.tile_row0 = c->cfg.tile_row0;
 	fp.tile_rows = c->cfg.tile_rows;
+	fp.strip_rows = c->cfg.strip_rows;
+	fp.strip_count = c->cfg.strip_count;
+	fp.strip_index = c->cfg.strip_index;
 	fp.n_slots = c->cfg.ray_queue_buffer_size;
 
 	const float px = (c->sun_x - 0.0f) * 6.28f, py = (c->sun_y - 0.5f) * 3.14f;
@@ -626,7 +629,13 @@ int bm_create(bm_context** out, const bm_config* cfg) {
 		return fail_api(BM_E_INVALID, "bm_create: grid dimensions must be positive multiples of 128");
 	if (!cfg->screen_width || !cfg->screen_height || !cfg->ray_queue_buffer_size || cfg->brick_load_queue_size <= 0)
 		return fail_api(BM_E_INVALID, "bm_create: zero-sized image or queue");
-	if (cfg->tile_rows && cfg->tile_row0 + cfg->tile_rows > cfg->screen_height) return fail_api(BM_E_INVALID, "bm_create: tile exceeds the image");
+	if (cfg->tile_rows && !cfg->strip_rows && cfg->tile_row0 + cfg->tile_rows > cfg->screen_height) return fail_api(BM_E_INVALID, "bm_create: tile exceeds the image");
+	if (cfg->strip_rows) {
+		if (!cfg->strip_count || cfg->strip_index >= cfg->strip_count || !cfg->tile_rows) return fail_api(BM_E_INVALID, "bm_create: bad strip partition");
+		const uint32_t last = cfg->tile_rows - 1;
+		const uint32_t y = ((last / cfg->strip_rows) * cfg->strip_count + cfg->strip_index) * cfg->strip_rows + last % cfg->strip_rows;
+		if (y >= cfg->screen_height) return fail_api(BM_E_INVALID, "bm_create: strip partition exceeds the image");
+	}
 	bm_context* c = new (std::nothrow) bm_context();
 	if (!c) return fail_api(BM_E_NOMEM, "bm_create: out of host memory");
 	c->cfg = *cfg;

@@ -45,6 +45,17 @@ def tile_rows_for_rank(height, rank, world_size):
     return row0, base + (1 if rank < extra else 0)
 
 
+def strip_rows_for_rank(height, rank, world_size, strip=8):
+    """Interleaved partition: strips of `strip` rows dealt round-robin to the ranks. Returns (rows_owned, image_rows) where
+    image_rows[r] is the image row behind row r of the rank's accumulation buffer (same formula as bm_config.strip_*)."""
+    rows = []
+    s = rank
+    while s * strip < height:
+        rows.extend(range(s * strip, min((s + 1) * strip, height)))
+        s += world_size
+    return len(rows), np.array(rows, dtype=np.int64)
+
+
 class SceneStore:
     """Device-resident world in the reference's layout (Scene.h:21-31) plus the streaming step (Scene.cpp:200-229)."""
 

@@ -83,6 +83,11 @@ typedef struct bm_config {
 	 * [tile_row0, tile_row0 + tile_rows) of the full image. tile_rows == 0 means the whole image. The
 	 * accumulation buffer handed to bm_* then covers only the tile (tile_rows * screen_width pixels). */
 	uint32_t tile_row0, tile_rows;
+	/* Interleaved partition (better load balance than one contiguous band: sky rows finish their paths after one segment,
+	 * terrain rows need up to four). strip_rows != 0: the image is cut into strips of strip_rows rows and this context owns
+	 * strips strip_index, strip_index + strip_count, ...; tile_rows is then the number of rows it owns (tile_row0 is ignored)
+	 * and row r of its accumulation buffer is image row ((r / strip_rows) * strip_count + strip_index) * strip_rows + r % strip_rows. */
+	uint32_t strip_rows, strip_count, strip_index;
 } bm_config;
 
 /* Camera fields read by launch_kernels (camera.h:4-9; kernel.cu:384-387,416). */

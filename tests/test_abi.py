@@ -78,6 +78,19 @@ def test_product_does_not_import_the_oracle():
                 assert m is None, "%s references the oracle: %r" % (f, m.group(0))
 
 
+def test_strip_partition_covers_the_image_once():
+    for h, n, strip in ((1080, 1, 8), (1080, 2, 8), (1080, 8, 8), (1083, 4, 8), (2160, 8, 16)):
+        owned = [bm.strip_rows_for_rank(h, r, n, strip) for r in range(n)]
+        allrows = np.sort(np.concatenate([rows for _, rows in owned]))
+        assert np.array_equal(allrows, np.arange(h))
+        for r, (cnt, rows) in enumerate(owned):
+            assert cnt == len(rows)
+            k = np.arange(cnt)
+            assert np.array_equal(rows, ((k // strip) * n + r) * strip + k % strip), "python helper and bm_config.strip_* formula agree"
+        counts = [c for c, _ in owned]
+        assert max(counts) - min(counts) <= strip
+
+
 def test_tile_partition():
     for h, n in ((1080, 1), (1080, 2), (1080, 7), (2160, 8)):
         bands = [bm.tile_rows_for_rank(h, r, n) for r in range(n)]

@@ -308,6 +308,32 @@ def test_tiles_compose_like_independent_renderers(oracle, golden):
     assert agree > 0.99, "band and full image disagree on hit/miss for %.2f%% of pixels" % (100 * (1 - agree))
 
 
+def test_interleaved_strips_cover_the_image(golden, stores):
+    """bm_config.strip_*: two contexts owning alternating 8-row strips see, per pixel, the geometry of the full-image run."""
+    g = golden("256")
+    w, h = int(g["width"]), int(g["height"])
+    cfg_full = cfg_from_golden(g)
+    ren_full = renderer_for(g, stores("256"), cfg_full)
+    st_full = bm.State(cfg_full)
+    ren_full.launch_kernels(st_full)
+    full_hit = (st_full.rays("work")["distance"] < 1e20)[: w * h].reshape(h, w)
+    seen = np.zeros(h, bool)
+    for rank in range(2):
+        rows, image_rows = bm.strip_rows_for_rank(h, rank, 2, 8)
+        cfg = cfg_from_golden(g, tile_rows=rows, strip_rows=8, strip_count=2, strip_index=rank)
+        ren = renderer_for(g, stores("256"), cfg)
+        st = bm.State(cfg)
+        ren.launch_kernels(st)
+        rays = st.rays("work")[: rows * w]
+        assert np.array_equal(rays["pixel_index"], np.arange(rows * w, dtype=np.uint32)), "pixel index is local to the rank's buffer"
+        hit = (rays["distance"] < 1e20).reshape(rows, w)
+        agree = (hit == full_hit[image_rows]).mean()
+        assert agree > 0.99, "rank %d disagrees with the full image on %.2f%% of its pixels" % (rank, 100 * (1 - agree))
+        assert st.blit_buffer.shape == (rows, w, 4)
+        seen[image_rows] = True
+    assert seen.all()
+
+
 # ---- streaming ----------------------------------------------------------------------------------------------------
 def test_streaming_matches_oracle_as_sets(oracle, golden, stores):
     """From an empty device scene: requests (as sorted sets, P4 of SURVEY 8c), index words modulo slot numbers, radiance."""
