@@ -113,13 +113,15 @@ struct SceneView {
 	int32_t* load_queue;          // GPUScene.brick_load_queue
 	uint32_t* load_queue_count;   // GPUScene.brick_load_queue_count
 	uint32_t* flat_indices;       // != nullptr: indices[sc] == flat_indices + sc * 4096 (verified at bind time)
-	const uint32_t* coarse;       // emptiness bitmap, 1 bit per block of (1 << coarse_shift)^3 cells (global copy)
+	const uint32_t* coarse;       // emptiness bitmap, 1 bit per block of (1 << coarse_shift)^3 cells (global copy; the kernels
+	                              // work on a shared-memory copy). Bit (bx & 31) of word ((bz * coarse_nby + by) << coarse_wshift) + (bx >> 5):
+	                              // rows are padded to a power-of-two number of words so that the address is two shifts and one IMAD
 	int cells, cells_height;      // variables.h:17-18
 	int supergrid_xy;             // variables.h:12
 	float grid_size_f, grid_height_f;
 	int lod2, lod8;               // variables.h:25-27
 	uint32_t queue_size;          // variables.h:35
-	int coarse_shift, coarse_nx, coarse_nxy;  // bitmap geometry
+	int coarse_shift, coarse_nby, coarse_wshift;  // bitmap geometry
 	uint32_t coarse_words;
 	const uint32_t* fine;         // emptiness per cell: 64 bits per 4x4x4 block, bit (x&3) | (y&3)<<2 | (z&3)<<4 (global)
 	int fine_nx, fine_nxy;        // 4x4x4 blocks per row / per slab
@@ -247,8 +249,7 @@ __device__ __forceinline__ bool intersect_aabb(const SceneView& sv, const F3& o,
 	return gmin(hi.x, gmin(hi.y, hi.z)) > tmin;
 }
 
-// intersect_voxel, voxel.cuh:135-261. `coarse_smem` is the block's shared-memory copy of the emptiness bitmap
-// (nullptr: read every index word like the reference). The DDA performs exactly the reference's sequence of
+// intersect_voxel, voxel.cuh:135-261. `coarse_smem` is the block's shared-memory copy of the emptiness bitmap. The DDA performs exactly the reference's sequence of
 // floating-point steps; only the LOADS of index words inside empty blocks are skipped.
 template <bool COUNT>
 __device__ __forceinline__ bool intersect_voxel(const SceneView& sv, const uint32_t* coarse_smem, F3 origin, const F3 direction, F3& normal,
@@ -274,20 +275,21 @@ __device__ __forceinline__ bool intersect_voxel(const SceneView& sv, const uint3
 	dda_setup(origin, direction, a);
 	if (a.pos.x < 0 || a.pos.x >= sv.cells || a.pos.y < 0 || a.pos.y >= sv.cells || a.pos.z < 0 || a.pos.z >= sv.cells_height) return false;
 	const I3 lim{ sv.cells, sv.cells, sv.cells_height };
+	const uint32_t coarse_saddr = (uint32_t)__cvta_generic_to_shared(coarse_smem);
 
 	int step_axis = -1;
 	for (;;) {
 		// Is the cell possibly non-empty? Shared-memory bitmap over blocks of cells first, then one bit per cell (global).
-		bool maybe = true;
 		if (COUNT) wc->steps++;
-		if (coarse_smem) {
-			const int cb = (a.pos.x >> sv.coarse_shift) + (a.pos.y >> sv.coarse_shift) * sv.coarse_nx + (a.pos.z >> sv.coarse_shift) * sv.coarse_nxy;
-			maybe = (coarse_smem[cb >> 5] >> (cb & 31)) & 1u;
-			if (maybe) {
-				const int fb = (a.pos.x >> 2) + (a.pos.y >> 2) * sv.fine_nx + (a.pos.z >> 2) * sv.fine_nxy;
-				const int bit = (a.pos.x & 3) | ((a.pos.y & 3) << 2) | ((a.pos.z & 3) << 4);
-				maybe = (__ldg(sv.fine + (size_t)fb * 2 + (bit >> 5)) >> (bit & 31)) & 1u;
-			}
+		const int bx = a.pos.x >> sv.coarse_shift;
+		const int row = (a.pos.z >> sv.coarse_shift) * sv.coarse_nby + (a.pos.y >> sv.coarse_shift);
+		uint32_t cw;  // explicit shared-window load: keeps the address arithmetic to one shift-add per step
+		asm("ld.shared.u32 %0, [%1];" : "=r"(cw) : "r"(coarse_saddr + (((row << sv.coarse_wshift) + (bx >> 5)) << 2)));
+		bool maybe = (cw >> (bx & 31)) & 1u;
+		if (maybe) {
+			const int fb = (a.pos.x >> 2) + (a.pos.y >> 2) * sv.fine_nx + (a.pos.z >> 2) * sv.fine_nxy;
+			const int bit = (a.pos.x & 3) | ((a.pos.y & 3) << 2) | ((a.pos.z & 3) << 4);
+			maybe = (__ldg(sv.fine + (size_t)fb * 2 + (bit >> 5)) >> (bit & 31)) & 1u;
 		}
 		if (maybe) {
 			const int sc = (a.pos.x >> 4) + (a.pos.y >> 4) * sv.supergrid_xy + (a.pos.z >> 4) * sv.supergrid_xy * sv.supergrid_xy;  // voxel.cuh:197

@@ -107,6 +107,21 @@ __device__ __forceinline__ void store_shadow(bm_shadow* q, const F3& o, const F3
 	q->pixel_index = pixel;
 }
 
+constexpr int kShadowQueue = 64;  // per-warp shadow-ray queue entries (structure of arrays, 10 words per entry)
+
+template <bool COUNT>
+__device__ __forceinline__ void trace_shadow(const SceneView& sv, const uint32_t* coarse, const FrameParams& fp, const FrameIO& io, const float* q, uint32_t e,
+                                             WorkCounters& wc, unsigned long long& n_unocc) {
+	const F3 o{ q[0 * kShadowQueue + e], q[1 * kShadowQueue + e], q[2 * kShadowQueue + e] };
+	const F3 d{ q[3 * kShadowQueue + e], q[4 * kShadowQueue + e], q[5 * kShadowQueue + e] };
+	F3 y{ 0.f, 0.f, 0.f };  // kernel.cu:337-338
+	float t = 0.f;
+	if (!intersect_voxel<COUNT>(sv, coarse, o, d, y, t, fp.cam_cell, &wc)) {
+		accum_add(io.accum, __float_as_uint(q[9 * kShadowQueue + e]), q[6 * kShadowQueue + e], q[7 * kShadowQueue + e], q[8 * kShadowQueue + e], 0.f);
+		n_unocc++;
+	}
+}
+
 // ---- the frame kernel: one thread owns one slot from ray generation / survivor fetch through extend, shade and its shadow
 // ray. RECORD (bm_launch_frame) additionally leaves every buffer the reference's five kernels leave; COUNT fills the work
 // counters. Warps pull runs of 128 consecutive slots; there is no block-level synchronisation inside a frame.
@@ -115,11 +130,8 @@ __global__ void __launch_bounds__(kTile, 4) frame_kernel(const FrameParams fp, c
 	extern __shared__ uint32_t s_coarse[];
 	DeviceState* st = io.st;
 	if (st->done) return;
-	const uint32_t* coarse = nullptr;
-	if (sv.coarse) {
-		for (uint32_t i = threadIdx.x; i < sv.coarse_words; i += blockDim.x) s_coarse[i] = __ldg(sv.coarse + i);
-		coarse = s_coarse;
-	}
+	for (uint32_t i = threadIdx.x; i < sv.coarse_words; i += blockDim.x) s_coarse[i] = __ldg(sv.coarse + i);
+	const uint32_t* coarse = s_coarse;
 	__syncthreads();
 
 	const uint32_t c = st->primary_ray_cnt;
@@ -132,6 +144,8 @@ __global__ void __launch_bounds__(kTile, 4) frame_kernel(const FrameParams fp, c
 	// kernel, kernel.cu:158,228,245,330); no block-level synchronisation inside the frame
 	constexpr uint32_t kRun = 4;
 	const uint32_t lane = threadIdx.x & 31;
+	float* q = reinterpret_cast<float*>(s_coarse + sv.coarse_words) + (threadIdx.x >> 5) * (10 * kShadowQueue);  // this warp's shadow-ray queue
+	uint32_t qn = 0;                                                                                               // entries queued (warp-uniform)
 	const uint32_t nruns = (fp.n_slots + kRun * 32 - 1) / (kRun * 32);
 	uint32_t run = 0, round = kRun;
 	for (;;) {
@@ -164,15 +178,26 @@ __global__ void __launch_bounds__(kTile, 4) frame_kernel(const FrameParams fp, c
 			if (s.add_radiance) accum_add(io.accum, ray.pixel_index, s.radiance.x, s.radiance.y, s.radiance.z, 1.f);
 			else if (s.terminated) accum_add(io.accum, ray.pixel_index, 0.f, 0.f, 0.f, 1.f);
 			n_term += s.terminated;
-			// connect, kernel.cu:328-346
+		}
+		// connect, kernel.cu:328-346. Only about half of the lanes come out of shade with a shadow ray, so the rays are queued
+		// per warp in shared memory and traced 32 at a time: the shadow traversal always runs with a full warp. (Which thread
+		// traces a shadow ray does not matter: it only adds to the accumulation buffer, kernel.cu:341-343.)
+		{
+			const uint32_t hm = __ballot_sync(0xFFFFFFFFu, has_shadow);
 			if (has_shadow) {
-				F3 y{ 0.f, 0.f, 0.f };
-				float t = 0.f;
+				const uint32_t e = qn + __popc(hm & ((1u << lane) - 1u));
+				q[0 * kShadowQueue + e] = ray.origin.x; q[1 * kShadowQueue + e] = ray.origin.y; q[2 * kShadowQueue + e] = ray.origin.z;
+				q[3 * kShadowQueue + e] = shadow_dir.x; q[4 * kShadowQueue + e] = shadow_dir.y; q[5 * kShadowQueue + e] = shadow_dir.z;
+				q[6 * kShadowQueue + e] = shadow_color.x; q[7 * kShadowQueue + e] = shadow_color.y; q[8 * kShadowQueue + e] = shadow_color.z;
+				q[9 * kShadowQueue + e] = __uint_as_float(ray.pixel_index);
+			}
+			qn += __popc(hm);
+			__syncwarp();
+			if (qn >= 32) {
+				qn -= 32;
+				trace_shadow<COUNT>(sv, coarse, fp, io, q, qn + lane, wc, n_unocc);
 				n_shadow++;
-				if (!intersect_voxel<COUNT>(sv, coarse, ray.origin, shadow_dir, y, t, fp.cam_cell, &wc)) {
-					accum_add(io.accum, ray.pixel_index, shadow_color.x, shadow_color.y, shadow_color.z, 0.f);
-					n_unocc++;
-				}
+				__syncwarp();
 			}
 		}
 		if (survives) store_ray(io.out + slot, ray);
@@ -183,6 +208,11 @@ __global__ void __launch_bounds__(kTile, 4) frame_kernel(const FrameParams fp, c
 			const uint32_t hmask = __ballot_sync(0xFFFFFFFFu, has_shadow);
 			if (lane == 0) io.shadow_mask[slot >> 5] = hmask;
 		}
+	}
+
+	if (lane < qn) {  // the last, partial batch of shadow rays
+		trace_shadow<COUNT>(sv, coarse, fp, io, q, lane, wc, n_unocc);
+		n_shadow++;
 	}
 
 	// per-warp statistics -> a handful of atomics per warp
@@ -382,25 +412,26 @@ __global__ void __launch_bounds__(1024) requests_merge_kernel(const SceneView sv
 	if (threadIdx.x == 0) *sv.load_queue_count = s_total;  // may exceed q, consumers clamp (kernel.cu:409)
 }
 
-// emptiness bitmap: bit b set iff any index word of coarse block b is non-zero
-__global__ void coarse_build_kernel(const SceneView sv, uint32_t* coarse, uint32_t nblocks) {
-	const uint32_t b = blockIdx.x * blockDim.x + threadIdx.x;
+// emptiness bitmap: one warp per word (32 consecutive blocks in x), bit set iff any index word of the block is non-zero
+__global__ void coarse_build_kernel(const SceneView sv, uint32_t* coarse) {
+	const uint32_t gid = blockIdx.x * blockDim.x + threadIdx.x;
+	const uint32_t word = gid >> 5, lane = gid & 31;
+	if (word >= sv.coarse_words) return;
 	const int side = 1 << sv.coarse_shift;
+	const int row = word >> sv.coarse_wshift, bx = ((word & ((1u << sv.coarse_wshift) - 1u)) << 5) + lane;
+	const int by = row % sv.coarse_nby, bz = row / sv.coarse_nby;
 	bool any = false;
-	if (b < nblocks) {
-		const int bx = b % sv.coarse_nx, by = (b / sv.coarse_nx) % (sv.coarse_nxy / sv.coarse_nx), bz = b / sv.coarse_nxy;
-		for (int z = 0; z < side && !any; z++)
-			for (int y = 0; y < side && !any; y++)
-				for (int x = 0; x < side; x++) {
-					const int px = bx * side + x, py = by * side + y, pz = bz * side + z;
-					if (px >= sv.cells || py >= sv.cells || pz >= sv.cells_height) continue;
-					const int sc = (px >> 4) + (py >> 4) * sv.supergrid_xy + (pz >> 4) * sv.supergrid_xy * sv.supergrid_xy;
-					const int local = (px & 15) + (py & 15) * 16 + (pz & 15) * 256;
-					if (sv.indices[sc][local]) { any = true; break; }
-				}
-	}
+	for (int z = 0; z < side && !any; z++)
+		for (int y = 0; y < side && !any; y++)
+			for (int x = 0; x < side; x++) {
+				const int px = bx * side + x, py = by * side + y, pz = bz * side + z;
+				if (px >= sv.cells || py >= sv.cells || pz >= sv.cells_height) continue;
+				const int sc = (px >> 4) + (py >> 4) * sv.supergrid_xy + (pz >> 4) * sv.supergrid_xy * sv.supergrid_xy;
+				const int local = (px & 15) + (py & 15) * 16 + (pz & 15) * 256;
+				if (sv.indices[sc][local]) { any = true; break; }
+			}
 	const uint32_t ballot = __ballot_sync(0xFFFFFFFFu, any);
-	if ((threadIdx.x & 31) == 0 && (b >> 5) < sv.coarse_words) coarse[b >> 5] = ballot;
+	if (lane == 0) coarse[word] = ballot;
 }
 
 // per-cell emptiness, 64 bits per 4x4x4 block of cells
@@ -433,11 +464,8 @@ __global__ void flat_check_kernel(uint32_t* const* indices, uint32_t n, uint32_t
 
 __global__ void trace_kernel(const SceneView sv, I3 cam, size_t n, const float* origins, const float* directions, float* normals, float* distances, uint8_t* hits) {
 	extern __shared__ uint32_t s_coarse[];
-	const uint32_t* coarse = nullptr;
-	if (sv.coarse) {
-		for (uint32_t i = threadIdx.x; i < sv.coarse_words; i += blockDim.x) s_coarse[i] = __ldg(sv.coarse + i);
-		coarse = s_coarse;
-	}
+	for (uint32_t i = threadIdx.x; i < sv.coarse_words; i += blockDim.x) s_coarse[i] = __ldg(sv.coarse + i);
+	const uint32_t* coarse = s_coarse;
 	__syncthreads();
 	for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
 		F3 nrm{ normals[3 * i], normals[3 * i + 1], normals[3 * i + 2] };
@@ -697,26 +725,26 @@ int bm_scene_bind(bm_context* c, bm_gpu_scene scene) {
 	sv.lod2 = c->cfg.lod_distance_2x2x2;
 	sv.lod8 = c->cfg.lod_distance_8x8x8;
 	sv.queue_size = (uint32_t)c->cfg.brick_load_queue_size;
-	// emptiness bitmap: the finest block size whose bitmap fits in 64 KiB of shared memory
-	int shift = 0;
-	uint64_t bits;
+	// emptiness bitmap: the finest block size whose bitmap (rows padded to a power-of-two number of words) fits in 64 KiB of
+	// shared memory
+	int shift = 0, wshift = 0;
+	uint64_t words;
 	for (;; shift++) {
-		const uint64_t nx = (uint64_t)(sv.cells + (1 << shift) - 1) >> shift, nz = (uint64_t)(sv.cells_height + (1 << shift) - 1) >> shift;
-		bits = nx * nx * nz;
-		if (bits <= 64u * 1024u * 8u) break;
+		const uint64_t nb = (uint64_t)(sv.cells + (1 << shift) - 1) >> shift, nz = (uint64_t)(sv.cells_height + (1 << shift) - 1) >> shift;
+		for (wshift = 0; (32ull << wshift) < nb; wshift++) {}
+		words = (nz * nb) << wshift;
+		if (words * 4 <= 64u * 1024u) break;
 	}
 	sv.coarse_shift = shift;
-	sv.coarse_nx = (sv.cells + (1 << shift) - 1) >> shift;
-	sv.coarse_nxy = sv.coarse_nx * sv.coarse_nx;
-	sv.coarse_words = (uint32_t)((bits + 31) / 32);
+	sv.coarse_nby = (sv.cells + (1 << shift) - 1) >> shift;
+	sv.coarse_wshift = wshift;
+	sv.coarse_words = (uint32_t)words;
 	cudaFree(c->d_coarse);
 	c->d_coarse = nullptr;
-	CK(cudaMalloc(&c->d_coarse, (size_t)(sv.coarse_words + 1) * 4));
-	CK(cudaMemsetAsync(c->d_coarse, 0, (size_t)(sv.coarse_words + 1) * 4, c->stream));
+	CK(cudaMalloc(&c->d_coarse, (size_t)sv.coarse_words * 4));
 	sv.coarse = nullptr;
 	sv.flat_indices = nullptr;
-	const uint32_t nblocks = (uint32_t)bits;
-	coarse_build_kernel<<<(sv.coarse_words * 32 + 255) / 256, 256, 0, c->stream>>>(sv, c->d_coarse, nblocks);
+	coarse_build_kernel<<<(sv.coarse_words * 32 + 255) / 256, 256, 0, c->stream>>>(sv, c->d_coarse);
 	CK(cudaGetLastError());
 	sv.fine = nullptr;
 	sv.fine_nx = (sv.cells + 3) >> 2;
@@ -742,7 +770,7 @@ int bm_scene_bind(bm_context* c, bm_gpu_scene scene) {
 	sv.fine = c->d_fine;
 	sv.flat_indices = not_flat ? nullptr : first;
 	// launch geometry of the persistent frame kernel
-	c->frame_smem = (size_t)sv.coarse_words * 4;
+	c->frame_smem = (size_t)sv.coarse_words * 4 + (size_t)(kTile / 32) * 10 * kShadowQueue * 4;  // emptiness bitmap + per-warp shadow queues
 	CK(cudaFuncSetAttribute(frame_kernel<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)c->frame_smem));
 	CK(cudaFuncSetAttribute(frame_kernel<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)c->frame_smem));
 	CK(cudaFuncSetAttribute(frame_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)c->frame_smem));

@@ -418,6 +418,60 @@ def test_request_merge_kernel_matches_specification(golden):
     assert not any(word(p) & 0x20000000 for p in dropped), "dropped requests are released for a later frame"
 
 
+# ---- caves world (BASELINE config 4 at a size the oracle can build) + LoD + tone map ------------------------------------
+def test_caves_world_streaming_with_lod_matches_oracle(oracle, lib):
+    """A sparse 3-D cave world (not in the reference: integer lattice noise, identical in the oracle and on the device),
+    LoD thresholds small enough that all three branches of voxel.cuh:212-227 run, everything streamed in from an empty
+    device scene through the request queue."""
+    cfg = bm.default_config(grid_size=512, grid_height=256, lod_distance_2x2x2=150, lod_distance_8x8x8=900, brick_load_queue_size=1024,
+                            ray_queue_buffer_size=131072, screen_width=384, screen_height=256)
+    store = bm.SceneStore(cfg, kind=R.SCENE_CAVES, seed=7, resident=False)
+    osc = ob.OracleScene(oracle, 512, 256, 150, 900, 1024).generate_caves(seed=7)
+    assert store.total_bricks > 1000
+    for sc in range(store.superchunks):
+        assert np.array_equal(store.indices(sc, host_view=True), osc.host_indices(sc)), "cave generator differs in superchunk %d" % sc
+        assert np.array_equal(store.bricks(sc), osc.host_bricks(sc))
+    pos, d = (-40.0, 250.0, 120.0), np.array([0.94, 0.1, 0.05], np.float32)
+    d = (d / np.sqrt((d.astype(np.float64) ** 2).sum())).astype(np.float32)
+    ren = bm.Renderer(cfg, store)
+    ren.set_camera(bm.make_camera(position=pos, direction=d))
+    oren = ob.OracleRenderer(osc, 384, 256, 131072, ob.make_camera(position=pos, direction=d))
+    state = bm.State(cfg)
+    total_requests = 0
+    for f in range(1, 6):
+        ren.launch_kernels(state)
+        cnt, rpos = ren.load_queue()
+        store.process_load_queue(ren.stream)
+        state.swap()
+        if f > 1:
+            osc.stream()
+        oren.frame(threads=1)
+        ocnt, opos = osc.queue()
+        assert cnt == ocnt
+        if cnt <= 1024:
+            assert sorted(map(tuple, rpos)) == sorted(map(tuple, opos))
+        total_requests += min(cnt, 1024)
+        c = ren.counters()
+        assert [c.primary_ray_cnt, c.shadow_ray_cnt] == [oren.state.primary_ray_cnt, oren.state.shadow_ray_cnt]
+    assert total_requests > 100 and oren.stats.lod_bytes > 0, "the view must exercise streaming and the 2x2x2 LoD"
+    assert_close_rel(state.blit_buffer.cpu().numpy(), oren.accum, RADIANCE_TOL, "cave world accumulation")
+
+
+def test_tonemap_matches_oracle(oracle, golden, stores):
+    """bm_tonemap == blit_onto_framebuffer's colour math (kernel.cu:355-362): rgb / alpha, gamma 1/2.2, alpha 1."""
+    g = golden("256")
+    ren = renderer_for(g, stores("256"))
+    blit = torch.zeros(int(g["height"]), int(g["width"]), 4, dtype=torch.float32, device="cuda")
+    ren.render(blit, 4)
+    got = ren.tonemap(blit).cpu().numpy()
+    acc = blit.cpu().numpy()
+    want = np.zeros_like(acc)
+    oracle.lib.orc_tonemap(acc.ctypes.data, acc.shape[0] * acc.shape[1], want.ctypes.data)
+    ok = acc[..., 3] > 0
+    assert ok.mean() > 0.9
+    assert_close_rel(got[ok], want[ok], 1e-5, "tone-mapped image")
+
+
 # ---- against the live reference -------------------------------------------------------------------------------------
 @pytest.mark.skipif(not ob.Reference.available("256"), reason="oracle/_ref not built")
 def test_drop_in_on_the_reference_hosts_own_scene(golden):
