@@ -123,7 +123,16 @@ def run_reference(args, rank, world):
         return
     import torch
     ref = ob.Reference("4096", WIDTH, HEIGHT, device=0)
-    ref.generate()
+    # Scene::generate prints timing lines with std::cout (Scene.cpp:149,192); keep stdout to the one JSON line
+    sys.stdout.flush()
+    saved = os.dup(1)
+    os.dup2(2, 1)
+    try:
+        ref.generate()
+    finally:
+        sys.stdout.flush()
+        os.dup2(saved, 1)
+        os.close(saved)
     ref.force_resident()
     ref.set_camera(ob.make_camera(position=CAM_POS, direction=CAM_DIR))
     ref.set_sun(*SUN)
