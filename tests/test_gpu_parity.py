@@ -247,6 +247,54 @@ def test_throughput_kernel_matches_simple_kernel_on_adversarial_rays(golden, sto
     assert [sf[k] for k in ("shadow_rays", "terminations", "unoccluded")] == [ss[k] for k in ("shadow_rays", "terminations", "unoccluded")]
 
 
+def test_ragged_sizes_match_oracle(oracle, golden):
+    """Slot count not a multiple of the warp size or of a run, image not a multiple of anything, fewer slots than pixels and
+    more slots than pixels (the cursor wraps inside a frame, kernel.cu:170-171)."""
+    g = golden("256")
+    for n_slots, w, h in ((100003, 333, 211), (50021, 401, 97)):
+        cfg = cfg_from_golden(g, )
+        cfg.ray_queue_buffer_size, cfg.screen_width, cfg.screen_height = n_slots, w, h
+        store = bm.SceneStore(cfg, resident=True)
+        ren = bm.Renderer(cfg, store)
+        ren.set_camera(bm.make_camera(position=g["cam_pos"], direction=g["cam_dir"]))
+        s = ob.OracleScene(oracle, 256, 256).generate_terrain().set_residency(True)
+        oren = ob.OracleRenderer(s, w, h, n_slots, ob.make_camera(position=g["cam_pos"], direction=g["cam_dir"]))
+        state = bm.State(cfg)
+        blit = torch.zeros(h, w, 4, dtype=torch.float32, device="cuda")
+        ren2 = bm.Renderer(cfg, store)
+        ren2.set_camera(bm.make_camera(position=g["cam_pos"], direction=g["cam_dir"]))
+        for f in range(4):
+            ren.launch_kernels(state)
+            oren.frame()
+            c = ren.counters()
+            assert [c.primary_ray_cnt, c.shadow_ray_cnt, c.start_position] == [oren.state.primary_ray_cnt, oren.state.shadow_ray_cnt, oren.state.start_position]
+            assert_records_equal(state.rays("next", c.primary_ray_cnt), oren.rays[: c.primary_ray_cnt], what="survivors, n_slots=%d frame %d" % (n_slots, f + 1))
+            state.swap()
+        ren2.render(blit, 4)
+        assert_close_rel(state.blit_buffer.cpu().numpy(), oren.accum, RADIANCE_TOL, "accumulation n_slots=%d" % n_slots)
+        assert_close_rel(blit.cpu().numpy(), oren.accum, RADIANCE_TOL, "fused accumulation n_slots=%d" % n_slots)
+        store.close()
+
+
+def test_host_buffer_entry_point(golden, stores):
+    """bm_render_to_host / bm_read_requests: results land in HOST buffers (pinned), as the e2e leg of bench.py uses them."""
+    g = golden("256")
+    cfg = cfg_from_golden(g)
+    store = bm.SceneStore(cfg, resident=False)
+    ren = renderer_for(g, store, cfg)
+    h, w, q = int(g["height"]), int(g["width"]), cfg.brick_load_queue_size
+    blit = torch.zeros(h, w, 4, dtype=torch.float32, device="cuda")
+    accum_host = torch.zeros(h, w, 4, dtype=torch.float32).pin_memory()
+    cnt_host = torch.zeros(1, dtype=torch.int32).pin_memory()
+    pos_host = torch.zeros(q, 3, dtype=torch.int32).pin_memory()
+    ren.render_to_host(blit, 1, accum_host, request_count_host=cnt_host, request_positions_host=pos_host)
+    assert torch.equal(accum_host, blit.cpu())
+    assert int(cnt_host[0]) == int(g["stream1_count"])
+    assert sorted(map(tuple, pos_host[: int(cnt_host[0])].numpy())) == sorted(map(tuple, g["stream1_positions"]))
+    cnt, pos = ren.load_queue()
+    assert cnt == int(cnt_host[0]) and np.array_equal(pos, pos_host[:cnt].numpy())
+
+
 def test_work_counters_match_oracle(oracle, golden, stores):
     """S (cell steps), K (bricks entered), P, V of SURVEY 8d, which feed the roofline's algorithmic bytes."""
     g = golden("256")
