@@ -249,11 +249,17 @@ __device__ __forceinline__ bool intersect_aabb(const SceneView& sv, const F3& o,
 	return gmin(hi.x, gmin(hi.y, hi.z)) > tmin;
 }
 
-// intersect_voxel, voxel.cuh:135-261. `coarse_smem` is the block's shared-memory copy of the emptiness bitmap. The DDA performs exactly the reference's sequence of
-// floating-point steps; only the LOADS of index words inside empty blocks are skipped.
-template <bool COUNT>
-__device__ __forceinline__ bool intersect_voxel(const SceneView& sv, const uint32_t* coarse_smem, F3 origin, const F3 direction, F3& normal,
-                                                float& distance, const I3 cam, WorkCounters* wc) {
+// State of a cell-level traversal between two calls of trace_run: everything intersect_voxel keeps in locals across its
+// DDA loop (voxel.cuh:157-190). tdelta and the integer steps are functions of the direction alone.
+struct TraceState {
+	F3 origin;      // ray origin in cell units, after the AABB entry adjustment (voxel.cuh:142-157)
+	float tminn;    // voxel.cuh:136
+	Dda a;          // cell-level DDA
+	int step_axis;  // last stepped axis, -1 = none yet
+};
+
+// intersect_voxel up to its DDA loop (voxel.cuh:136-190). Returns false when the ray misses outright.
+__device__ __forceinline__ bool trace_setup(const SceneView& sv, F3 origin, const F3 direction, F3& normal, TraceState& ts) {
 	float tminn;
 	if (!intersect_aabb(sv, origin, direction, tminn)) return false;
 
@@ -271,14 +277,32 @@ __device__ __forceinline__ bool intersect_voxel(const SceneView& sv, const uint3
 	}
 
 	origin = F3{ origin.x * 0.125f, origin.y * 0.125f, origin.z * 0.125f };  // origin /= 8.f
-	Dda a;
-	dda_setup(origin, direction, a);
-	if (a.pos.x < 0 || a.pos.x >= sv.cells || a.pos.y < 0 || a.pos.y >= sv.cells || a.pos.z < 0 || a.pos.z >= sv.cells_height) return false;
+	dda_setup(origin, direction, ts.a);
+	if (ts.a.pos.x < 0 || ts.a.pos.x >= sv.cells || ts.a.pos.y < 0 || ts.a.pos.y >= sv.cells || ts.a.pos.z < 0 || ts.a.pos.z >= sv.cells_height) return false;
+	ts.origin = origin;
+	ts.tminn = tminn;
+	ts.step_axis = -1;
+	return true;
+}
+
+enum : int { TRACE_MISS = 0, TRACE_HIT = 1, TRACE_SUSPENDED = 2 };
+
+// The DDA loop of intersect_voxel (voxel.cuh:192-259). `coarse_smem` is the block's shared-memory copy of the emptiness
+// bitmap. The DDA performs exactly the reference's sequence of floating-point steps; only the LOADS of index words for empty
+// cells are skipped. BOUNDED: give up after `budget` cell tests and return TRACE_SUSPENDED with the state to resume from (the
+// cell the ray stands in has not been tested yet).
+template <bool COUNT, bool BOUNDED>
+__device__ __forceinline__ int trace_run(const SceneView& sv, const uint32_t* coarse_smem, const F3 direction, F3& normal, float& distance, const I3 cam,
+                                         TraceState& ts, int budget, WorkCounters* wc) {
+	const F3 origin = ts.origin;
+	const float tminn = ts.tminn;
+	Dda& a = ts.a;
+	int& step_axis = ts.step_axis;
 	const I3 lim{ sv.cells, sv.cells, sv.cells_height };
 	const uint32_t coarse_saddr = (uint32_t)__cvta_generic_to_shared(coarse_smem);
 
-	int step_axis = -1;
-	for (;;) {
+	bool left_world = false;
+	for (int it = 0; !BOUNDED || it < budget; it++) {
 		// Is the cell possibly non-empty? Shared-memory bitmap over blocks of cells first, then one bit per cell (global).
 		if (COUNT) wc->steps++;
 		const int bx = a.pos.x >> sv.coarse_shift;
@@ -308,13 +332,13 @@ __device__ __forceinline__ bool intersect_voxel(const SceneView& sv, const uint3
 				float sub_distance = 0.f;
 				if (lod_distance_squared > sv.lod8) {  // voxel.cuh:212-214
 					distance = new_distance * 8.f + tminn;
-					return true;
+					return TRACE_HIT;
 				} else if (lod_distance_squared > sv.lod2) {  // voxel.cuh:215-220
 					const F3 x{ fmaf(direction.x, new_distance, origin.x), fmaf(direction.y, new_distance, origin.y), fmaf(direction.z, new_distance, origin.z) };
 					const F3 so{ fmaf(normal.x * 0.2f, -kEpsilon, x.x + x.x), fmaf(normal.y * 0.2f, -kEpsilon, x.y + x.y), fmaf(normal.z * 0.2f, -kEpsilon, x.z + x.z) };
 					if (intersect_byte(so, direction, normal, sub_distance, (index & BM_BRICK_LOD_BITS) >> 12)) {
 						distance = (new_distance * 8.f + sub_distance * 4.f) + tminn;
-						return true;
+						return TRACE_HIT;
 					}
 				} else if (index & BM_BRICK_LOADED_BIT) {  // voxel.cuh:222-227
 					const bm_brick* p = sv.bricks[sc] + (index & BM_BRICK_INDEX_BITS);
@@ -323,7 +347,7 @@ __device__ __forceinline__ bool intersect_voxel(const SceneView& sv, const uint3
 					const F3 so{ x.x * 8.f - normal.x * kEpsilon, x.y * 8.f - normal.y * kEpsilon, x.z * 8.f - normal.z * kEpsilon };
 					if (intersect_brick(so, direction, normal, sub_distance, p)) {
 						distance = (new_distance * 8.f + sub_distance) + tminn;
-						return true;
+						return TRACE_HIT;
 					}
 				} else if (index & BM_BRICK_UNLOADED_BIT) {  // voxel.cuh:228-244
 					const uint32_t old = atomicOr(word, BM_BRICK_REQUESTED_BIT);
@@ -339,13 +363,26 @@ __device__ __forceinline__ bool intersect_voxel(const SceneView& sv, const uint3
 						}
 					}
 					distance = new_distance * 8.f + tminn;
-					return true;
+					return TRACE_HIT;
 				}
 			}
 		}
-		if (!dda_advance(a, lim, step_axis)) break;
+		if (!dda_advance(a, lim, step_axis)) {
+			left_world = true;
+			break;
+		}
 	}
-	return false;
+	return (BOUNDED && !left_world) ? TRACE_SUSPENDED : TRACE_MISS;
+}
+
+
+// intersect_voxel, voxel.cuh:135-261
+template <bool COUNT>
+__device__ __forceinline__ bool intersect_voxel(const SceneView& sv, const uint32_t* coarse_smem, const F3 origin, const F3 direction, F3& normal,
+                                                float& distance, const I3 cam, WorkCounters* wc) {
+	TraceState ts;
+	if (!trace_setup(sv, origin, direction, normal, ts)) return false;
+	return trace_run<COUNT, false>(sv, coarse_smem, direction, normal, distance, cam, ts, 0, wc) == TRACE_HIT;
 }
 
 // ---- sun-sky model (sunsky.cu) -------------------------------------------------------------------------------

@@ -1,0 +1,233 @@
+// frame_kernel_q: the throughput form of one frame. Same results as frame_kernel (bit for bit on everything geometric).
+//
+// Why: in frame_kernel a warp traces 32 rays until the LONGEST of them ends; on the benchmark workload that leaves 43 % of
+// the lanes busy (ray lengths: median 79 cell steps, 90th percentile 215, maximum 830). Here a lane traces for at most
+// `quantum` cell steps at a time. A ray that has not ended by then is SUSPENDED: its traversal state (position, tmax, axis --
+// tdelta and the step signs are recomputed from the direction) and its payload go into the warp's work queue in shared memory,
+// and the warp goes on with rays that are at the same stage: whenever 32 suspended rays have piled up they are resumed
+// together, otherwise the warp starts 32 fresh slots. Replaying the measured length distribution gives 76 % busy lanes at a
+// quantum of 64 and 86 % at 32. Shadow rays go through the same queue (they are born into it by shade), so they too are
+// traced 32 at a time and in quanta. Suspending never changes a result: the DDA state is saved and restored exactly.
+//
+// One queue entry = 20 words, structure of arrays per warp, 64 entries (a batch pops at most 32 and every lane pushes at most
+// one entry per batch: the ray it had to suspend, or the shadow ray its shaded vertex produced).
+#pragma once
+
+namespace bm {
+
+constexpr int kQBlock = 1024;      // 32 warps, one block per SM (shared memory: bitmap + 32 queues = 192 KiB)
+constexpr int kQueueEntries = 64;
+enum : int {
+	E_OX = 0, E_OY, E_OZ,   // trace-space origin in cell units (continuations) / world-space origin (new shadow rays)
+	E_DX, E_DY, E_DZ,       // direction
+	E_POS,                  // cell position, 10 bits per axis, last stepped axis + 1 in the top two bits
+	E_TX, E_TY, E_TZ,       // tmax
+	E_TMIN,                 // tminn
+	E_FLAGS,                // kind | bounces << 2
+	E_WX, E_WY, E_WZ,       // world-space origin of an extend ray (shading needs it)
+	E_CX, E_CY, E_CZ,       // throughput of an extend ray / colour of a shadow ray
+	E_PIXEL, E_SLOT,
+	E_WORDS
+};
+enum : int { K_NONE = -1, K_EXTEND = 0, K_SHADOW = 1, K_SHADOW_NEW = 2 };
+
+#define QF(field, e) q[(field) * kQueueEntries + (e)]
+#define QU(field, e) reinterpret_cast<uint32_t*>(q)[(field) * kQueueEntries + (e)]
+
+__global__ void __launch_bounds__(kQBlock, 1) frame_kernel_q(const FrameParams fp, const SceneView sv, const FrameIO io, const int quantum) {
+	extern __shared__ uint32_t s_coarse[];
+	DeviceState* st = io.st;
+	if (st->done) return;
+	for (uint32_t i = threadIdx.x; i < sv.coarse_words; i += blockDim.x) s_coarse[i] = __ldg(sv.coarse + i);
+	const uint32_t* coarse = s_coarse;
+	__syncthreads();
+
+	const uint32_t c = st->primary_ray_cnt;
+	const uint32_t start = st->start_position;
+	const uint32_t frame = st->frame;
+	const uint32_t lane = threadIdx.x & 31;
+	const uint32_t lt_mask = (1u << lane) - 1u;
+	float* q = reinterpret_cast<float*>(s_coarse + sv.coarse_words) + (threadIdx.x >> 5) * (E_WORDS * kQueueEntries);
+	uint32_t qn = 0;  // entries in the warp's queue (warp-uniform)
+	uint32_t n_shadow = 0, n_term = 0, n_unocc = 0;
+
+	constexpr uint32_t kRun = 4;  // warps pull runs of kRun * 32 consecutive slots with one atomic
+	const uint32_t nruns = (fp.n_slots + kRun * 32 - 1) / (kRun * 32);
+	uint32_t run = 0, round = kRun;
+	bool pool_dry = false;
+
+	for (;;) {
+		int kind = K_NONE;
+		int status = TRACE_MISS;
+		bool tracing = false;
+		TraceState ts;
+		F3 direction{ 0.f, 0.f, 1.f }, normal{ 0.f, 0.f, 0.f }, world{ 0.f, 0.f, 0.f }, payload{ 0.f, 0.f, 0.f };
+		float distance = kVeryFar;
+		uint32_t pixel = 0, slot = 0;
+		int bounces = 0;
+
+		if (qn >= 32 || (pool_dry && qn > 0)) {
+			// ---- resume a batch of queued rays --------------------------------------------------------------------------
+			const uint32_t take = min(qn, 32u);
+			qn -= take;
+			if (lane < take) {
+				const uint32_t e = qn + lane;
+				const uint32_t flags = QU(E_FLAGS, e);
+				kind = (int)(flags & 3u);
+				bounces = (int)(flags >> 2);
+				direction = F3{ QF(E_DX, e), QF(E_DY, e), QF(E_DZ, e) };
+				payload = F3{ QF(E_CX, e), QF(E_CY, e), QF(E_CZ, e) };
+				pixel = QU(E_PIXEL, e);
+				if (kind == K_SHADOW_NEW) {
+					// connect, kernel.cu:328-346: origin = shaded hit point, normal y{} = 0, t = 0
+					kind = K_SHADOW;
+					tracing = trace_setup(sv, F3{ QF(E_OX, e), QF(E_OY, e), QF(E_OZ, e) }, direction, normal, ts);
+				} else {
+					if (kind == K_EXTEND) {
+						world = F3{ QF(E_WX, e), QF(E_WY, e), QF(E_WZ, e) };
+						slot = QU(E_SLOT, e);
+					}
+					// the traversal state exactly as it was saved; tdelta and the integer steps as dda_setup derives them
+					ts.origin = F3{ QF(E_OX, e), QF(E_OY, e), QF(E_OZ, e) };
+					ts.tminn = QF(E_TMIN, e);
+					const uint32_t packed = QU(E_POS, e);
+					ts.a.pos = I3{ (int)(packed & 1023u), (int)((packed >> 10) & 1023u), (int)((packed >> 20) & 1023u) };
+					ts.step_axis = (int)(packed >> 30) - 1;
+					ts.a.tmax = F3{ QF(E_TX, e), QF(E_TY, e), QF(E_TZ, e) };
+					const F3 step{ gsign(direction.x), gsign(direction.y), gsign(direction.z) };
+					ts.a.stepi = I3{ (int)step.x, (int)step.y, (int)step.z };
+					const F3 rdinv{ direction.x == 0.0f ? 0.0f : 1.f / direction.x, direction.y == 0.0f ? 0.0f : 1.f / direction.y,
+						            direction.z == 0.0f ? 0.0f : 1.f / direction.z };
+					ts.a.tdelta = F3{ step.x * rdinv.x, step.y * rdinv.y, step.z * rdinv.z };
+					tracing = true;
+				}
+			}
+		} else if (!pool_dry) {
+			// ---- start 32 fresh slots ---------------------------------------------------------------------------------------
+			if (round == kRun) {
+				if (lane == 0) run = atomicAdd(&st->tile_ticket, 1u);
+				run = __shfl_sync(0xFFFFFFFFu, run, 0);
+				round = 0;
+				if (run >= nruns) {
+					pool_dry = true;
+					continue;
+				}
+			}
+			slot = (run * kRun + round) * 32 + lane;
+			round++;
+			if (slot < fp.n_slots) {
+				Ray ray;
+				if (slot < c) ray = load_ray(survivor_ptr(io, slot));
+				else ray = generate_primary(fp, frame, start, slot - c);  // primary_rays, kernel.cu:154-223
+				kind = K_EXTEND;
+				world = ray.origin;
+				direction = ray.direction;
+				payload = ray.throughput;
+				normal = ray.normal;
+				pixel = ray.pixel_index;
+				bounces = ray.bounces;
+				tracing = trace_setup(sv, ray.origin, ray.direction, normal, ts);  // extend, kernel.cu:226-238
+			}
+		} else {
+			break;
+		}
+		__syncwarp();  // every popped entry has been read before anything is pushed
+
+		// ---- one quantum of traversal -------------------------------------------------------------------------------------
+		WorkCounters wc;
+		if (tracing) status = trace_run<false, true>(sv, coarse, direction, normal, distance, fp.cam_cell, ts, quantum, &wc);
+		__syncwarp();  // lanes whose ray ended early wait here: they are shaded together, not interleaved with the tracing lanes
+
+		// ---- outcomes -----------------------------------------------------------------------------------------------------
+		int push = K_NONE;  // what this lane appends to the queue
+		F3 push_o{ 0.f, 0.f, 0.f }, push_d{ 0.f, 0.f, 0.f }, push_c{ 0.f, 0.f, 0.f };
+		if (kind != K_NONE) {
+			if (status == TRACE_SUSPENDED) {
+				push = kind;
+			} else if (kind == K_SHADOW) {
+				if (status == TRACE_MISS) {  // kernel.cu:340-344
+					accum_add(io.accum, pixel, payload.x, payload.y, payload.z, 0.f);
+					n_unocc++;
+				}
+			} else {
+				// shade, kernel.cu:242-325
+				Ray ray;
+				ray.origin = world;
+				ray.direction = direction;
+				ray.throughput = payload;
+				ray.normal = normal;
+				ray.distance = status == TRACE_HIT ? distance : kVeryFar;
+				ray.identifier = 0;
+				ray.bounces = bounces;
+				ray.pixel_index = pixel;
+				const ShadeResult s = shade_vertex(fp, frame, slot, ray);
+				if (s.add_radiance) accum_add(io.accum, pixel, s.radiance.x, s.radiance.y, s.radiance.z, 1.f);
+				else if (s.terminated) accum_add(io.accum, pixel, 0.f, 0.f, 0.f, 1.f);
+				n_term += s.terminated;
+				if (s.survives) {
+					store_ray(io.out + slot, ray);
+					atomicOr(io.out_mask + (slot >> 5), 1u << (slot & 31));
+				}
+				if (s.has_shadow) {
+					n_shadow++;
+					push = K_SHADOW_NEW;
+					push_o = ray.origin;
+					push_d = s.shadow_dir;
+					push_c = s.shadow_color;
+				}
+			}
+		}
+#ifdef BM_QDEBUG
+		{
+			const uint32_t tm = __ballot_sync(0xFFFFFFFFu, tracing), sm = __ballot_sync(0xFFFFFFFFu, tracing && status == TRACE_SUSPENDED);
+			const uint32_t km = __ballot_sync(0xFFFFFFFFu, kind != K_NONE);
+			if (lane == 0) {
+				atomicAdd(&st->index_reads, 1ull);
+				atomicAdd(&st->cell_steps, (unsigned long long)__popc(tm));
+				atomicAdd(&st->bricks, (unsigned long long)__popc(sm));
+				atomicAdd(&st->requests, (unsigned long long)__popc(km));
+			}
+		}
+#endif
+		const uint32_t pm = __ballot_sync(0xFFFFFFFFu, push != K_NONE);
+		if (push != K_NONE) {
+			const uint32_t e = qn + __popc(pm & lt_mask);
+			if (push == K_SHADOW_NEW) {
+				QF(E_OX, e) = push_o.x; QF(E_OY, e) = push_o.y; QF(E_OZ, e) = push_o.z;
+				QF(E_DX, e) = push_d.x; QF(E_DY, e) = push_d.y; QF(E_DZ, e) = push_d.z;
+				QF(E_CX, e) = push_c.x; QF(E_CY, e) = push_c.y; QF(E_CZ, e) = push_c.z;
+				QU(E_FLAGS, e) = (uint32_t)K_SHADOW_NEW;
+				QU(E_PIXEL, e) = pixel;
+			} else {
+				QF(E_OX, e) = ts.origin.x; QF(E_OY, e) = ts.origin.y; QF(E_OZ, e) = ts.origin.z;
+				QF(E_DX, e) = direction.x; QF(E_DY, e) = direction.y; QF(E_DZ, e) = direction.z;
+				QU(E_POS, e) = (uint32_t)ts.a.pos.x | ((uint32_t)ts.a.pos.y << 10) | ((uint32_t)ts.a.pos.z << 20) | ((uint32_t)(ts.step_axis + 1) << 30);
+				QF(E_TX, e) = ts.a.tmax.x; QF(E_TY, e) = ts.a.tmax.y; QF(E_TZ, e) = ts.a.tmax.z;
+				QF(E_TMIN, e) = ts.tminn;
+				QU(E_FLAGS, e) = (uint32_t)push | ((uint32_t)bounces << 2);
+				QF(E_CX, e) = payload.x; QF(E_CY, e) = payload.y; QF(E_CZ, e) = payload.z;
+				QU(E_PIXEL, e) = pixel;
+				if (push == K_EXTEND) {
+					QF(E_WX, e) = world.x; QF(E_WY, e) = world.y; QF(E_WZ, e) = world.z;
+					QU(E_SLOT, e) = slot;
+				}
+			}
+		}
+		qn += __popc(pm);
+		__syncwarp();
+	}
+
+	// per-warp statistics -> a handful of atomics per warp
+	const unsigned long long a = warp_sum((unsigned long long)n_shadow), b = warp_sum((unsigned long long)n_term), u = warp_sum((unsigned long long)n_unocc);
+	if (lane == 0) {
+		if (a) atomicAdd(&st->shadow_rays, a);
+		if (b) atomicAdd(&st->terminations, b);
+		if (b) atomicAdd(&st->paths_since_reset, b);
+		if (u) atomicAdd(&st->unoccluded, u);
+	}
+}
+
+#undef QF
+#undef QU
+
+}  // namespace bm

@@ -236,6 +236,10 @@ __global__ void __launch_bounds__(kTile, 4) frame_kernel(const FrameParams fp, c
 	}
 }
 
+}  // namespace bm
+#include "bm_frame_quantum.cuh"
+namespace bm {
+
 // set_wavefront_globals (kernel.cu:122-139) + per-tile survivor counts (popcount of the slot masks) -> exclusive prefix.
 // One block. mask[ntiles * 8] -> prefix[ntiles + 1]; optional second pair for the shadow queue (RECORD). Also zeroes
 // `clear_mask`, the mask buffer the NEXT frame will write with atomicOr.
@@ -553,6 +557,11 @@ struct bm_context {
 	uint64_t timed_launches = 0;
 	int frame_blocks = 0;
 	size_t frame_smem = 0;
+	// throughput kernel (frame_kernel_q)
+	bool use_quantum = true;  // BRICKMAP_B200_SIMPLE_KERNEL=1 switches the throughput path back to frame_kernel
+	int quantum = 64;         // BRICKMAP_B200_QUANTUM
+	int q_blocks = 0;
+	size_t q_smem = 0;
 };
 
 static inline F3 h_cross(const F3& a, const F3& b) { return F3{ a.y * b.z - b.y * a.z, a.z * b.x - b.z * a.x, a.x * b.y - b.x * a.y }; }
@@ -780,6 +789,14 @@ int bm_scene_bind(bm_context* c, bm_gpu_scene scene) {
 	CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, frame_kernel<false, false>, kTile, c->frame_smem));
 	if (per_sm < 1) per_sm = 1;
 	c->frame_blocks = c->sm_count * per_sm;
+	if (const char* e = getenv("BRICKMAP_B200_SIMPLE_KERNEL")) c->use_quantum = e[0] != '1';
+	if (const char* e = getenv("BRICKMAP_B200_QUANTUM")) c->quantum = atoi(e) > 0 ? atoi(e) : c->quantum;
+	if (sv.cells > 1024 || sv.cells_height > 1024) c->use_quantum = false;  // queue entries pack a cell position into 3 x 10 bits
+	c->q_smem = (size_t)sv.coarse_words * 4 + (size_t)(kQBlock / 32) * E_WORDS * kQueueEntries * 4;
+	CK(cudaFuncSetAttribute(frame_kernel_q, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)c->q_smem));
+	CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, frame_kernel_q, kQBlock, c->q_smem));
+	if (per_sm < 1) c->use_quantum = false;
+	c->q_blocks = c->sm_count * (per_sm < 1 ? 1 : per_sm);
 	c->bound = true;
 	return 0;
 }
@@ -929,7 +946,8 @@ static int launch_frame_kernels(bm_context* c, const FrameIO& io, bool count) {
 		CK(cudaEventRecord(e0, c->stream));
 	}
 	if (count) frame_kernel<RECORD, true><<<blocks, kTile, c->frame_smem, c->stream>>>(c->fp, c->sv, io);
-	else frame_kernel<RECORD, false><<<blocks, kTile, c->frame_smem, c->stream>>>(c->fp, c->sv, io);
+	else if (RECORD || !c->use_quantum) frame_kernel<RECORD, false><<<blocks, kTile, c->frame_smem, c->stream>>>(c->fp, c->sv, io);
+	else frame_kernel_q<<<c->q_blocks, kQBlock, c->q_smem, c->stream>>>(c->fp, c->sv, io, c->quantum);
 	CK(cudaGetLastError());
 	if (c->timing) CK(cudaEventRecord(e1, c->stream));
 	// the mask that was this frame's input becomes the next frame's output: the scan clears it
