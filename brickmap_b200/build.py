@@ -12,7 +12,7 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 SOURCES = ["bm_kernels.cu", "bm_scene_store.cu"]
-HEADERS = ["bm_device.cuh", os.path.join("..", "..", "include", "brickmap_b200.h")]
+HEADERS = ["bm_device.cuh", "bm_frame_quantum.cuh", os.path.join("..", "..", "include", "brickmap_b200.h")]
 LIB = os.path.join(HERE, "libbrickmap_b200.so")
 NVCC_FLAGS = (["-DBM_QDEBUG"] if os.environ.get("BM_QDEBUG") else []) + ["-std=c++17", "-O3", "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-fmad=false",
               "-Xcompiler", "-fPIC", "-shared"]

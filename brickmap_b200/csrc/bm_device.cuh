@@ -12,6 +12,8 @@
 
 #include "../../include/brickmap_b200.h"
 
+extern __shared__ uint32_t bm_dyn_smem[];  // the kernels' dynamic shared memory starts with their copy of the emptiness bitmap
+
 namespace bm {
 
 constexpr float kPi = 3.1415926535897932f;  // variables.h:3
@@ -114,15 +116,20 @@ struct SceneView {
 	uint32_t* load_queue_count;   // GPUScene.brick_load_queue_count
 	uint32_t* flat_indices;       // != nullptr: indices[sc] == flat_indices + sc * 4096 (verified at bind time)
 	const uint32_t* coarse;       // emptiness bitmap, 1 bit per block of (1 << coarse_shift)^3 cells (global copy; the kernels
-	                              // work on a shared-memory copy). Bit (bx & 31) of word ((bz * coarse_nby + by) << coarse_wshift) + (bx >> 5):
-	                              // rows are padded to a power-of-two number of words so that the address is two shifts and one IMAD
+	                              // work on a shared-memory copy), with a BORDER of one block on every side whose bits are set.
+	                              // For a cell position p biased by one block (p' = p + (1 << coarse_shift)), b = p' >> coarse_shift:
+	                              // bit (b.x & 31) of word (b.z * coarse_nby + b.y) * coarse_roww + (b.x >> 5). The one cell a DDA can
+	                              // stand in outside the world falls into the border, so the empty-space loop needs no bounds test.
+	                              // Stored as PAIRS of words {near, far}: near = the bitmap above; far bit set iff the block and its 26
+	                              // neighbours are all empty (never for border blocks), i.e. every cell within Chebyshev distance 4 of
+	                              // any cell of the block is empty and inside the world
 	int cells, cells_height;      // variables.h:17-18
 	int supergrid_xy;             // variables.h:12
 	float grid_size_f, grid_height_f;
 	int lod2, lod8;               // variables.h:25-27
 	uint32_t queue_size;          // variables.h:35
-	int coarse_shift, coarse_nby, coarse_wshift;  // bitmap geometry
-	uint32_t coarse_words;
+	int coarse_shift, coarse_nby, coarse_roww;  // bitmap geometry (coarse_nby counts the border blocks, coarse_roww = words per row)
+	uint32_t coarse_words;        // words of ONE bitmap; the global array holds 2 * coarse_words
 	const uint32_t* fine;         // emptiness per cell: 64 bits per 4x4x4 block, bit (x&3) | (y&3)<<2 | (z&3)<<4 (global)
 	int fine_nx, fine_nxy;        // 4x4x4 blocks per row / per slab
 };
@@ -151,6 +158,19 @@ __device__ __forceinline__ void dda_setup(const F3& o, const F3& d, Dda& a) {
 	a.tmax = F3{ d.x != 0.f ? (cb.x - o.x) * rdinv.x : 1000000.f, d.y != 0.f ? (cb.y - o.y) * rdinv.y : 1000000.f,
 		         d.z != 0.f ? (cb.z - o.z) * rdinv.z : 1000000.f };
 	a.tdelta = F3{ step.x * rdinv.x, step.y * rdinv.y, step.z * rdinv.z };
+}
+
+// The set-up of a DDA nested in another one along the same ray (2x2x2 octants and 8x8x8 voxels inside a cell): the reference
+// recomputes sign(d) and 1/d (voxel.cuh:33-45 / 86-98); they are the parent's values, and 1/d == sign(d) * tdelta exactly.
+__device__ __forceinline__ void dda_setup_nested(const F3& o, const F3& d, const Dda& parent, Dda& a) {
+	a.pos = I3{ (int)o.x, (int)o.y, (int)o.z };
+	const F3 cb{ d.x > 0.f ? (float)(a.pos.x + 1) : (float)a.pos.x, d.y > 0.f ? (float)(a.pos.y + 1) : (float)a.pos.y,
+		         d.z > 0.f ? (float)(a.pos.z + 1) : (float)a.pos.z };
+	a.stepi = parent.stepi;
+	a.tdelta = parent.tdelta;
+	const F3 rdinv{ d.x < 0.f ? -a.tdelta.x : a.tdelta.x, d.y < 0.f ? -a.tdelta.y : a.tdelta.y, d.z < 0.f ? -a.tdelta.z : a.tdelta.z };
+	a.tmax = F3{ d.x != 0.f ? (cb.x - o.x) * rdinv.x : 1000000.f, d.y != 0.f ? (cb.y - o.y) * rdinv.y : 1000000.f,
+		         d.z != 0.f ? (cb.z - o.z) * rdinv.z : 1000000.f };
 }
 
 // One DDA step, voxel.cuh:66-74 / 122-130 / 249-258, hand-scheduled: 3 compares, 3 predicate ops, 3 predicated integer adds,
@@ -187,14 +207,62 @@ __device__ __forceinline__ bool dda_advance(Dda& a, const I3& lim, int& step_axi
 	return (unsigned)a.pos.x < (unsigned)lim.x && (unsigned)a.pos.y < (unsigned)lim.y && (unsigned)a.pos.z < (unsigned)lim.z;
 }
 
+// The same step without the bounds test (cell level: leaving the world is detected through the bitmap's border).
+__device__ __forceinline__ void dda_step(Dda& a, int& step_axis) {
+	asm("{\n\t"
+	    ".reg .pred pxy, pxz, pyz, mx, my, mz;\n\t"
+	    "setp.lt.f32 pxy, %3, %4;\n\t"
+	    "setp.lt.f32 pxz, %3, %5;\n\t"
+	    "setp.lt.f32 pyz, %4, %5;\n\t"
+	    "and.pred mx, pxy, pxz;\n\t"
+	    "not.pred pxy, pxy;\n\t"
+	    "and.pred my, pxy, pyz;\n\t"
+	    "or.pred mz, mx, my;\n\t"
+	    "not.pred mz, mz;\n\t"
+	    "@mx add.s32 %0, %0, %7;\n\t"
+	    "@my add.s32 %1, %1, %8;\n\t"
+	    "@mz add.s32 %2, %2, %9;\n\t"
+	    "@mx add.rn.f32 %3, %3, %10;\n\t"
+	    "@my add.rn.f32 %4, %4, %11;\n\t"
+	    "@mz add.rn.f32 %5, %5, %12;\n\t"
+	    "selp.s32 %6, 0, 2, mx;\n\t"
+	    "@my mov.s32 %6, 1;\n\t"
+	    "}"
+	    : "+r"(a.pos.x), "+r"(a.pos.y), "+r"(a.pos.z), "+f"(a.tmax.x), "+f"(a.tmax.y), "+f"(a.tmax.z), "=r"(step_axis)
+	    : "r"(a.stepi.x), "r"(a.stepi.y), "r"(a.stepi.z), "f"(a.tdelta.x), "f"(a.tdelta.y), "f"(a.tdelta.z));
+}
+
+// ... and without recording the axis (steps inside a run of cells known to be empty)
+__device__ __forceinline__ void dda_step_blind(Dda& a) {
+	asm("{\n\t"
+	    ".reg .pred pxy, pxz, pyz, mx, my, mz;\n\t"
+	    "setp.lt.f32 pxy, %3, %4;\n\t"
+	    "setp.lt.f32 pxz, %3, %5;\n\t"
+	    "setp.lt.f32 pyz, %4, %5;\n\t"
+	    "and.pred mx, pxy, pxz;\n\t"
+	    "not.pred pxy, pxy;\n\t"
+	    "and.pred my, pxy, pyz;\n\t"
+	    "or.pred mz, mx, my;\n\t"
+	    "not.pred mz, mz;\n\t"
+	    "@mx add.s32 %0, %0, %6;\n\t"
+	    "@my add.s32 %1, %1, %7;\n\t"
+	    "@mz add.s32 %2, %2, %8;\n\t"
+	    "@mx add.rn.f32 %3, %3, %9;\n\t"
+	    "@my add.rn.f32 %4, %4, %10;\n\t"
+	    "@mz add.rn.f32 %5, %5, %11;\n\t"
+	    "}"
+	    : "+r"(a.pos.x), "+r"(a.pos.y), "+r"(a.pos.z), "+f"(a.tmax.x), "+f"(a.tmax.y), "+f"(a.tmax.z)
+	    : "r"(a.stepi.x), "r"(a.stepi.y), "r"(a.stepi.z), "f"(a.tdelta.x), "f"(a.tdelta.y), "f"(a.tdelta.z));
+}
+
 __device__ __forceinline__ F3 axis_normal(const Dda& a, int axis) {  // normal[step_axis] = -step[step_axis]
 	return F3{ axis == 0 ? -(float)a.stepi.x : 0.f, axis == 1 ? -(float)a.stepi.y : 0.f, axis == 2 ? -(float)a.stepi.z : 0.f };
 }
 
 // voxel.cuh:26-77 (2x2x2 LoD octants)
-__device__ __forceinline__ bool intersect_byte(const F3& origin, const F3& direction, F3& normal, float& distance, uint32_t byte) {
+__device__ __forceinline__ bool intersect_byte(const F3& origin, const F3& direction, const Dda& parent, F3& normal, float& distance, uint32_t byte) {
 	Dda a;
-	dda_setup(origin, direction, a);
+	dda_setup_nested(origin, direction, parent, a);
 	const I3 lim{ 2, 2, 2 };
 	a.pos = I3{ a.pos.x % 2, a.pos.y % 2, a.pos.z % 2 };
 	distance = 0.f;
@@ -215,9 +283,9 @@ __device__ __forceinline__ bool intersect_byte(const F3& origin, const F3& direc
 
 // voxel.cuh:79-133 (8x8x8 voxel brick). The 64-byte brick is fetched once as four 128-bit loads; the DDA then
 // tests bits of the 8 z-slices held in registers instead of one dependent 4-byte global load per step.
-__device__ __forceinline__ bool intersect_brick(const F3& origin, const F3& direction, F3& normal, float& distance, const bm_brick* brick) {
+__device__ __forceinline__ bool intersect_brick(const F3& origin, const F3& direction, const Dda& parent, F3& normal, float& distance, const bm_brick* brick) {
 	Dda a;
-	dda_setup(origin, direction, a);
+	dda_setup_nested(origin, direction, parent, a);
 	const I3 lim{ 8, 8, 8 };
 	a.pos = I3{ a.pos.x % 8, a.pos.y % 8, a.pos.z % 8 };
 	distance = 0.f;
@@ -254,7 +322,7 @@ __device__ __forceinline__ bool intersect_aabb(const SceneView& sv, const F3& o,
 struct TraceState {
 	F3 origin;      // ray origin in cell units, after the AABB entry adjustment (voxel.cuh:142-157)
 	float tminn;    // voxel.cuh:136
-	Dda a;          // cell-level DDA
+	Dda a;          // cell-level DDA; a.pos is biased by one bitmap block (SceneView::coarse)
 	int step_axis;  // last stepped axis, -1 = none yet
 };
 
@@ -279,6 +347,8 @@ __device__ __forceinline__ bool trace_setup(const SceneView& sv, F3 origin, cons
 	origin = F3{ origin.x * 0.125f, origin.y * 0.125f, origin.z * 0.125f };  // origin /= 8.f
 	dda_setup(origin, direction, ts.a);
 	if (ts.a.pos.x < 0 || ts.a.pos.x >= sv.cells || ts.a.pos.y < 0 || ts.a.pos.y >= sv.cells || ts.a.pos.z < 0 || ts.a.pos.z >= sv.cells_height) return false;
+	const int bias = 1 << sv.coarse_shift;  // trace_run works on biased positions
+	ts.a.pos = I3{ ts.a.pos.x + bias, ts.a.pos.y + bias, ts.a.pos.z + bias };
 	ts.origin = origin;
 	ts.tminn = tminn;
 	ts.step_axis = -1;
@@ -289,88 +359,123 @@ enum : int { TRACE_MISS = 0, TRACE_HIT = 1, TRACE_SUSPENDED = 2 };
 
 // The DDA loop of intersect_voxel (voxel.cuh:192-259). `coarse_smem` is the block's shared-memory copy of the emptiness
 // bitmap. The DDA performs exactly the reference's sequence of floating-point steps; only the LOADS of index words for empty
-// cells are skipped. BOUNDED: give up after `budget` cell tests and return TRACE_SUSPENDED with the state to resume from (the
-// cell the ray stands in has not been tested yet).
-template <bool COUNT, bool BOUNDED>
+// cells are skipped, and the reference's per-step exit test (voxel.cuh:256) is made only where the bitmap says "maybe": the
+// bitmap's border catches the one position outside the world a DDA can reach. BOUNDED: give up after `budget` cell tests and
+// return TRACE_SUSPENDED with the state to resume from (the cell the ray stands in has not been tested yet; it may be the
+// cell outside the world, which the resumed loop then detects).
+// Inside the loop (and in a suspended TraceState) the cell position is BIASED by one bitmap block, see SceneView::coarse.
+// FAR: `coarse_smem` holds {near, far} word pairs; where the far bit is set the block's 26 neighbours are empty and inside the
+// world, so as many cells as a block is wide (4 in the stock world) lie ahead empty whatever the direction: the loop takes
+// that many DDA steps without a test, then one more whose cell the next iteration tests (a test costs more than a step).
+// STOCK: the bitmap geometry of the reference's stock world (512 x 512 x 64 cells: blocks of 4^3 cells, 130 rows of 5 words
+// per slab) as compile-time constants.
+template <bool COUNT, bool BOUNDED, bool FAR = false, bool STOCK = false>
 __device__ __forceinline__ int trace_run(const SceneView& sv, const uint32_t* coarse_smem, const F3 direction, F3& normal, float& distance, const I3 cam,
                                          TraceState& ts, int budget, WorkCounters* wc) {
 	const F3 origin = ts.origin;
 	const float tminn = ts.tminn;
 	Dda& a = ts.a;
 	int& step_axis = ts.step_axis;
-	const I3 lim{ sv.cells, sv.cells, sv.cells_height };
-	const uint32_t coarse_saddr = (uint32_t)__cvta_generic_to_shared(coarse_smem);
+	const int shift = STOCK ? 2 : sv.coarse_shift;
+	const int nby = STOCK ? 130 : sv.coarse_nby, roww = STOCK ? 5 : sv.coarse_roww;
+	const int bias = 1 << shift;
+	(void)coarse_smem;  // == bm_dyn_smem
+	uint32_t smem_base = (uint32_t)__cvta_generic_to_shared(bm_dyn_smem);  // shared-window address of the bitmap ...
+	asm volatile("" : "+r"(smem_base));  // ... pinned in a register (left alone the compiler re-derives it in every step)
 
 	bool left_world = false;
-	for (int it = 0; !BOUNDED || it < budget; it++) {
+	for (int it = budget; !BOUNDED || it > 0; it--) {
 		// Is the cell possibly non-empty? Shared-memory bitmap over blocks of cells first, then one bit per cell (global).
 		if (COUNT) wc->steps++;
-		const int bx = a.pos.x >> sv.coarse_shift;
-		const int row = (a.pos.z >> sv.coarse_shift) * sv.coarse_nby + (a.pos.y >> sv.coarse_shift);
-		uint32_t cw;  // explicit shared-window load: keeps the address arithmetic to one shift-add per step
-		asm("ld.shared.u32 %0, [%1];" : "=r"(cw) : "r"(coarse_saddr + (((row << sv.coarse_wshift) + (bx >> 5)) << 2)));
-		bool maybe = (cw >> (bx & 31)) & 1u;
-		if (maybe) {
-			const int fb = (a.pos.x >> 2) + (a.pos.y >> 2) * sv.fine_nx + (a.pos.z >> 2) * sv.fine_nxy;
-			const int bit = (a.pos.x & 3) | ((a.pos.y & 3) << 2) | ((a.pos.z & 3) << 4);
-			maybe = (__ldg(sv.fine + (size_t)fb * 2 + (bit >> 5)) >> (bit & 31)) & 1u;
-		}
-		if (maybe) {
-			const int sc = (a.pos.x >> 4) + (a.pos.y >> 4) * sv.supergrid_xy + (a.pos.z >> 4) * sv.supergrid_xy * sv.supergrid_xy;  // voxel.cuh:197
-			const int local = (a.pos.x & 15) + (a.pos.y & 15) * 16 + (a.pos.z & 15) * 256;                                        // voxel.cuh:198
-			uint32_t* word = sv.flat_indices ? sv.flat_indices + (((size_t)sc << 12) + local) : sv.indices[sc] + local;
-			const uint32_t index = __ldg(word);
-			if (COUNT) wc->index_reads++;
-			if (index) {
-				float new_distance = 0.f;
-				if (step_axis != -1) {
-					normal = axis_normal(a, step_axis);
-					new_distance = comp(a.tmax, step_axis) - comp(a.tdelta, step_axis);
-				}
-				const int dx = cam.x - a.pos.x, dy = cam.y - a.pos.y, dz = cam.z - a.pos.z;
-				const int lod_distance_squared = dx * dx + dy * dy + dz * dz;
-				float sub_distance = 0.f;
-				if (lod_distance_squared > sv.lod8) {  // voxel.cuh:212-214
-					distance = new_distance * 8.f + tminn;
-					return TRACE_HIT;
-				} else if (lod_distance_squared > sv.lod2) {  // voxel.cuh:215-220
-					const F3 x{ fmaf(direction.x, new_distance, origin.x), fmaf(direction.y, new_distance, origin.y), fmaf(direction.z, new_distance, origin.z) };
-					const F3 so{ fmaf(normal.x * 0.2f, -kEpsilon, x.x + x.x), fmaf(normal.y * 0.2f, -kEpsilon, x.y + x.y), fmaf(normal.z * 0.2f, -kEpsilon, x.z + x.z) };
-					if (intersect_byte(so, direction, normal, sub_distance, (index & BM_BRICK_LOD_BITS) >> 12)) {
-						distance = (new_distance * 8.f + sub_distance * 4.f) + tminn;
-						return TRACE_HIT;
+		const int bx = a.pos.x >> shift;
+		const int w = ((a.pos.z >> shift) * nby + (a.pos.y >> shift)) * roww + (bx >> 5);
+		uint32_t cw, fw = 0;
+		if (FAR) asm("ld.shared.v2.u32 {%0, %1}, [%2];" : "=r"(cw), "=r"(fw) : "r"(smem_base + (w << 3)));
+		else asm("ld.shared.u32 %0, [%1];" : "=r"(cw) : "r"(smem_base + (w << 2)));
+		uint32_t near_bit, far_bit;  // one mask, two AND-tests (the compiler's own form is shift + and + compare for each)
+		asm("{\n\t"
+		    ".reg .b32 m;\n\t"
+		    "shf.l.wrap.b32 m, 0, 1, %2;\n\t"
+		    "and.b32 %0, %3, m;\n\t"
+		    "and.b32 %1, %4, m;\n\t"
+		    "}"
+		    : "=r"(near_bit), "=r"(far_bit)
+		    : "r"(bx), "r"(cw), "r"(fw));
+		const bool far = FAR && !COUNT && far_bit;
+		if (near_bit) {
+			const I3 p{ a.pos.x - bias, a.pos.y - bias, a.pos.z - bias };
+			if ((unsigned)p.x >= (unsigned)sv.cells || (unsigned)p.y >= (unsigned)sv.cells || (unsigned)p.z >= (unsigned)sv.cells_height) {  // voxel.cuh:256
+				if (COUNT) wc->steps--;  // not a cell test of the reference: its loop ended with the step that left the world
+				left_world = true;
+				break;
+			}
+			const int fb = (p.x >> 2) + (p.y >> 2) * sv.fine_nx + (p.z >> 2) * sv.fine_nxy;
+			const int fbit = (p.x & 3) | ((p.y & 3) << 2) | ((p.z & 3) << 4);
+			if ((__ldg(sv.fine + (size_t)fb * 2 + (fbit >> 5)) >> (fbit & 31)) & 1u) {
+				const int sc = (p.x >> 4) + (p.y >> 4) * sv.supergrid_xy + (p.z >> 4) * sv.supergrid_xy * sv.supergrid_xy;  // voxel.cuh:197
+				const int local = (p.x & 15) + (p.y & 15) * 16 + (p.z & 15) * 256;                                        // voxel.cuh:198
+				uint32_t* word = sv.flat_indices ? sv.flat_indices + (((size_t)sc << 12) + local) : sv.indices[sc] + local;
+				const uint32_t index = __ldg(word);
+				if (COUNT) wc->index_reads++;
+				if (index) {
+					float new_distance = 0.f;
+					if (step_axis != -1) {
+						normal = axis_normal(a, step_axis);
+						new_distance = comp(a.tmax, step_axis) - comp(a.tdelta, step_axis);
 					}
-				} else if (index & BM_BRICK_LOADED_BIT) {  // voxel.cuh:222-227
-					const bm_brick* p = sv.bricks[sc] + (index & BM_BRICK_INDEX_BITS);
-					if (COUNT) wc->bricks++;
-					const F3 x{ fmaf(direction.x, new_distance, origin.x), fmaf(direction.y, new_distance, origin.y), fmaf(direction.z, new_distance, origin.z) };
-					const F3 so{ x.x * 8.f - normal.x * kEpsilon, x.y * 8.f - normal.y * kEpsilon, x.z * 8.f - normal.z * kEpsilon };
-					if (intersect_brick(so, direction, normal, sub_distance, p)) {
-						distance = (new_distance * 8.f + sub_distance) + tminn;
+					const int dx = cam.x - p.x, dy = cam.y - p.y, dz = cam.z - p.z;
+					const int lod_distance_squared = dx * dx + dy * dy + dz * dz;
+					float sub_distance = 0.f;
+					if (lod_distance_squared > sv.lod8) {  // voxel.cuh:212-214
+						distance = new_distance * 8.f + tminn;
 						return TRACE_HIT;
-					}
-				} else if (index & BM_BRICK_UNLOADED_BIT) {  // voxel.cuh:228-244
-					const uint32_t old = atomicOr(word, BM_BRICK_REQUESTED_BIT);
-					if (!(old & BM_BRICK_REQUESTED_BIT)) {
-						const uint32_t load_index = atomicAdd(sv.load_queue_count, 1u);
-						if (load_index < sv.queue_size) {
-							sv.load_queue[3 * load_index + 0] = a.pos.x;
-							sv.load_queue[3 * load_index + 1] = a.pos.y;
-							sv.load_queue[3 * load_index + 2] = a.pos.z;
-							if (COUNT) wc->requests++;
-						} else {
-							atomicAnd(word, ~BM_BRICK_REQUESTED_BIT);
+					} else if (lod_distance_squared > sv.lod2) {  // voxel.cuh:215-220
+						const F3 x{ fmaf(direction.x, new_distance, origin.x), fmaf(direction.y, new_distance, origin.y), fmaf(direction.z, new_distance, origin.z) };
+						const F3 so{ fmaf(normal.x * 0.2f, -kEpsilon, x.x + x.x), fmaf(normal.y * 0.2f, -kEpsilon, x.y + x.y), fmaf(normal.z * 0.2f, -kEpsilon, x.z + x.z) };
+						if (intersect_byte(so, direction, a, normal, sub_distance, (index & BM_BRICK_LOD_BITS) >> 12)) {
+							distance = (new_distance * 8.f + sub_distance * 4.f) + tminn;
+								return TRACE_HIT;
 						}
+					} else if (index & BM_BRICK_LOADED_BIT) {  // voxel.cuh:222-227
+						const bm_brick* b = sv.bricks[sc] + (index & BM_BRICK_INDEX_BITS);
+						if (COUNT) wc->bricks++;
+						const F3 x{ fmaf(direction.x, new_distance, origin.x), fmaf(direction.y, new_distance, origin.y), fmaf(direction.z, new_distance, origin.z) };
+						const F3 so{ x.x * 8.f - normal.x * kEpsilon, x.y * 8.f - normal.y * kEpsilon, x.z * 8.f - normal.z * kEpsilon };
+						if (intersect_brick(so, direction, a, normal, sub_distance, b)) {
+							distance = (new_distance * 8.f + sub_distance) + tminn;
+								return TRACE_HIT;
+						}
+					} else if (index & BM_BRICK_UNLOADED_BIT) {  // voxel.cuh:228-244
+						const uint32_t old = atomicOr(word, BM_BRICK_REQUESTED_BIT);
+						if (!(old & BM_BRICK_REQUESTED_BIT)) {
+							const uint32_t load_index = atomicAdd(sv.load_queue_count, 1u);
+							if (load_index < sv.queue_size) {
+								sv.load_queue[3 * load_index + 0] = p.x;
+								sv.load_queue[3 * load_index + 1] = p.y;
+								sv.load_queue[3 * load_index + 2] = p.z;
+								if (COUNT) wc->requests++;
+							} else {
+								atomicAnd(word, ~BM_BRICK_REQUESTED_BIT);
+							}
+						}
+						distance = new_distance * 8.f + tminn;
+						return TRACE_HIT;
 					}
-					distance = new_distance * 8.f + tminn;
-					return TRACE_HIT;
 				}
 			}
 		}
-		if (!dda_advance(a, lim, step_axis)) {
-			left_world = true;
-			break;
+		if (far) {
+			// the block's neighbours are as wide as the block: that many steps stay inside the empty neighbourhood
+			if (STOCK) {
+				dda_step_blind(a);
+				dda_step_blind(a);
+				dda_step_blind(a);
+				dda_step_blind(a);
+			} else {
+				for (int k = bias < 8 ? bias : 8; k > 0; k--) dda_step_blind(a);
+			}
 		}
+		dda_step(a, step_axis);
 	}
 	return (BOUNDED && !left_world) ? TRACE_SUSPENDED : TRACE_MISS;
 }

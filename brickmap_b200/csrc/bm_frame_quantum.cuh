@@ -15,15 +15,15 @@
 
 namespace bm {
 
-constexpr int kQBlock = 1024;      // 32 warps, one block per SM (shared memory: bitmap + 32 queues = 192 KiB)
+constexpr int kQBlock = 768;       // 24 warps, one block per SM (shared memory: near/far bitmap pairs 92 KiB + 24 queues 120 KiB)
 constexpr int kQueueEntries = 64;
 enum : int {
 	E_OX = 0, E_OY, E_OZ,   // trace-space origin in cell units (continuations) / world-space origin (new shadow rays)
 	E_DX, E_DY, E_DZ,       // direction
-	E_POS,                  // cell position, 10 bits per axis, last stepped axis + 1 in the top two bits
+	E_POS,                  // (biased) cell position x | y << 16; z is in E_FLAGS
 	E_TX, E_TY, E_TZ,       // tmax
 	E_TMIN,                 // tminn
-	E_FLAGS,                // kind | bounces << 2
+	E_FLAGS,                // kind | (last stepped axis + 1) << 2 | cell position z << 4 (12 bits) | bounces << 16
 	E_WX, E_WY, E_WZ,       // world-space origin of an extend ray (shading needs it)
 	E_CX, E_CY, E_CZ,       // throughput of an extend ray / colour of a shadow ray
 	E_PIXEL, E_SLOT,
@@ -34,11 +34,13 @@ enum : int { K_NONE = -1, K_EXTEND = 0, K_SHADOW = 1, K_SHADOW_NEW = 2 };
 #define QF(field, e) q[(field) * kQueueEntries + (e)]
 #define QU(field, e) reinterpret_cast<uint32_t*>(q)[(field) * kQueueEntries + (e)]
 
+template <bool STOCK, bool FAR>
 __global__ void __launch_bounds__(kQBlock, 1) frame_kernel_q(const FrameParams fp, const SceneView sv, const FrameIO io, const int quantum) {
 	extern __shared__ uint32_t s_coarse[];
 	DeviceState* st = io.st;
 	if (st->done) return;
-	for (uint32_t i = threadIdx.x; i < sv.coarse_words; i += blockDim.x) s_coarse[i] = __ldg(sv.coarse + i);
+	if (FAR) for (uint32_t i = threadIdx.x; i < 2 * sv.coarse_words; i += blockDim.x) s_coarse[i] = __ldg(sv.coarse + i);  // {near, far} pairs
+	else for (uint32_t i = threadIdx.x; i < sv.coarse_words; i += blockDim.x) s_coarse[i] = __ldg(sv.coarse + 2 * i);    // near words only
 	const uint32_t* coarse = s_coarse;
 	__syncthreads();
 
@@ -47,7 +49,7 @@ __global__ void __launch_bounds__(kQBlock, 1) frame_kernel_q(const FrameParams f
 	const uint32_t frame = st->frame;
 	const uint32_t lane = threadIdx.x & 31;
 	const uint32_t lt_mask = (1u << lane) - 1u;
-	float* q = reinterpret_cast<float*>(s_coarse + sv.coarse_words) + (threadIdx.x >> 5) * (E_WORDS * kQueueEntries);
+	float* q = reinterpret_cast<float*>(s_coarse + 2 * sv.coarse_words) + (threadIdx.x >> 5) * (E_WORDS * kQueueEntries);
 	uint32_t qn = 0;  // entries in the warp's queue (warp-uniform)
 	uint32_t n_shadow = 0, n_term = 0, n_unocc = 0;
 
@@ -74,7 +76,7 @@ __global__ void __launch_bounds__(kQBlock, 1) frame_kernel_q(const FrameParams f
 				const uint32_t e = qn + lane;
 				const uint32_t flags = QU(E_FLAGS, e);
 				kind = (int)(flags & 3u);
-				bounces = (int)(flags >> 2);
+				bounces = (int)(flags >> 16);
 				direction = F3{ QF(E_DX, e), QF(E_DY, e), QF(E_DZ, e) };
 				payload = F3{ QF(E_CX, e), QF(E_CY, e), QF(E_CZ, e) };
 				pixel = QU(E_PIXEL, e);
@@ -91,8 +93,8 @@ __global__ void __launch_bounds__(kQBlock, 1) frame_kernel_q(const FrameParams f
 					ts.origin = F3{ QF(E_OX, e), QF(E_OY, e), QF(E_OZ, e) };
 					ts.tminn = QF(E_TMIN, e);
 					const uint32_t packed = QU(E_POS, e);
-					ts.a.pos = I3{ (int)(packed & 1023u), (int)((packed >> 10) & 1023u), (int)((packed >> 20) & 1023u) };
-					ts.step_axis = (int)(packed >> 30) - 1;
+					ts.a.pos = I3{ (int)(packed & 0xFFFFu), (int)(packed >> 16), (int)((flags >> 4) & 0xFFFu) };
+					ts.step_axis = (int)((flags >> 2) & 3u) - 1;
 					ts.a.tmax = F3{ QF(E_TX, e), QF(E_TY, e), QF(E_TZ, e) };
 					const F3 step{ gsign(direction.x), gsign(direction.y), gsign(direction.z) };
 					ts.a.stepi = I3{ (int)step.x, (int)step.y, (int)step.z };
@@ -135,7 +137,7 @@ __global__ void __launch_bounds__(kQBlock, 1) frame_kernel_q(const FrameParams f
 
 		// ---- one quantum of traversal -------------------------------------------------------------------------------------
 		WorkCounters wc;
-		if (tracing) status = trace_run<false, true>(sv, coarse, direction, normal, distance, fp.cam_cell, ts, quantum, &wc);
+		if (tracing) status = trace_run<false, true, FAR, STOCK>(sv, coarse, direction, normal, distance, fp.cam_cell, ts, quantum, &wc);
 		__syncwarp();  // lanes whose ray ended early wait here: they are shaded together, not interleaved with the tracing lanes
 
 		// ---- outcomes -----------------------------------------------------------------------------------------------------
@@ -201,10 +203,10 @@ __global__ void __launch_bounds__(kQBlock, 1) frame_kernel_q(const FrameParams f
 			} else {
 				QF(E_OX, e) = ts.origin.x; QF(E_OY, e) = ts.origin.y; QF(E_OZ, e) = ts.origin.z;
 				QF(E_DX, e) = direction.x; QF(E_DY, e) = direction.y; QF(E_DZ, e) = direction.z;
-				QU(E_POS, e) = (uint32_t)ts.a.pos.x | ((uint32_t)ts.a.pos.y << 10) | ((uint32_t)ts.a.pos.z << 20) | ((uint32_t)(ts.step_axis + 1) << 30);
+				QU(E_POS, e) = (uint32_t)ts.a.pos.x | ((uint32_t)ts.a.pos.y << 16);
 				QF(E_TX, e) = ts.a.tmax.x; QF(E_TY, e) = ts.a.tmax.y; QF(E_TZ, e) = ts.a.tmax.z;
 				QF(E_TMIN, e) = ts.tminn;
-				QU(E_FLAGS, e) = (uint32_t)push | ((uint32_t)bounces << 2);
+				QU(E_FLAGS, e) = (uint32_t)push | ((uint32_t)(ts.step_axis + 1) << 2) | ((uint32_t)ts.a.pos.z << 4) | ((uint32_t)bounces << 16);
 				QF(E_CX, e) = payload.x; QF(E_CY, e) = payload.y; QF(E_CZ, e) = payload.z;
 				QU(E_PIXEL, e) = pixel;
 				if (push == K_EXTEND) {

@@ -130,7 +130,7 @@ __global__ void __launch_bounds__(kTile, 4) frame_kernel(const FrameParams fp, c
 	extern __shared__ uint32_t s_coarse[];
 	DeviceState* st = io.st;
 	if (st->done) return;
-	for (uint32_t i = threadIdx.x; i < sv.coarse_words; i += blockDim.x) s_coarse[i] = __ldg(sv.coarse + i);
+	for (uint32_t i = threadIdx.x; i < sv.coarse_words; i += blockDim.x) s_coarse[i] = __ldg(sv.coarse + 2 * i);  // near words only
 	const uint32_t* coarse = s_coarse;
 	__syncthreads();
 
@@ -416,15 +416,17 @@ __global__ void __launch_bounds__(1024) requests_merge_kernel(const SceneView sv
 	if (threadIdx.x == 0) *sv.load_queue_count = s_total;  // may exceed q, consumers clamp (kernel.cu:409)
 }
 
-// emptiness bitmap: one warp per word (32 consecutive blocks in x), bit set iff any index word of the block is non-zero
+// emptiness bitmap: one warp per word (32 consecutive blocks in x), bit set iff any index word of the block is non-zero;
+// block coordinates count from the one-block border, whose bits are all set (SceneView::coarse)
 __global__ void coarse_build_kernel(const SceneView sv, uint32_t* coarse) {
 	const uint32_t gid = blockIdx.x * blockDim.x + threadIdx.x;
 	const uint32_t word = gid >> 5, lane = gid & 31;
 	if (word >= sv.coarse_words) return;
 	const int side = 1 << sv.coarse_shift;
-	const int row = word >> sv.coarse_wshift, bx = ((word & ((1u << sv.coarse_wshift) - 1u)) << 5) + lane;
-	const int by = row % sv.coarse_nby, bz = row / sv.coarse_nby;
+	const int row = word / sv.coarse_roww, bx = (int)((word % sv.coarse_roww) << 5) + (int)lane - 1;
+	const int by = row % sv.coarse_nby - 1, bz = row / sv.coarse_nby - 1;
 	bool any = false;
+	if (bx < 0 || by < 0 || bz < 0 || bx * side >= sv.cells || by * side >= sv.cells || bz * side >= sv.cells_height) any = true;  // border (and row padding)
 	for (int z = 0; z < side && !any; z++)
 		for (int y = 0; y < side && !any; y++)
 			for (int x = 0; x < side; x++) {
@@ -435,7 +437,28 @@ __global__ void coarse_build_kernel(const SceneView sv, uint32_t* coarse) {
 				if (sv.indices[sc][local]) { any = true; break; }
 			}
 	const uint32_t ballot = __ballot_sync(0xFFFFFFFFu, any);
-	if (lane == 0) coarse[word] = ballot;
+	if (lane == 0) coarse[2 * word] = ballot;
+}
+
+// far words of the {near, far} pairs: block and its 26 neighbours all empty (SceneView::coarse). One thread per block bit.
+__global__ void far_build_kernel(const SceneView sv, uint32_t* coarse) {
+	const uint32_t gid = blockIdx.x * blockDim.x + threadIdx.x;
+	const uint32_t word = gid >> 5, lane = gid & 31;
+	if (word >= sv.coarse_words) return;
+	const int nbx = sv.coarse_roww * 32, nby = sv.coarse_nby, nbz = (int)(sv.coarse_words / (uint32_t)(sv.coarse_roww * sv.coarse_nby));
+	const int row = word / sv.coarse_roww, bx = (int)((word % sv.coarse_roww) << 5) + (int)lane;
+	const int by = row % nby, bz = row / nby;
+	bool far = true;
+	for (int dz = -1; dz <= 1 && far; dz++)
+		for (int dy = -1; dy <= 1 && far; dy++)
+			for (int dx = -1; dx <= 1; dx++) {
+				const int x = bx + dx, y = by + dy, z = bz + dz;
+				if (x < 0 || y < 0 || z < 0 || x >= nbx || y >= nby || z >= nbz) { far = false; break; }
+				const uint32_t w = coarse[2 * ((size_t)(z * nby + y) * sv.coarse_roww + (x >> 5))];
+				if ((w >> (x & 31)) & 1u) { far = false; break; }
+			}
+	const uint32_t ballot = __ballot_sync(0xFFFFFFFFu, far);
+	if (lane == 0) coarse[2 * word + 1] = ballot;
 }
 
 // per-cell emptiness, 64 bits per 4x4x4 block of cells
@@ -468,7 +491,7 @@ __global__ void flat_check_kernel(uint32_t* const* indices, uint32_t n, uint32_t
 
 __global__ void trace_kernel(const SceneView sv, I3 cam, size_t n, const float* origins, const float* directions, float* normals, float* distances, uint8_t* hits) {
 	extern __shared__ uint32_t s_coarse[];
-	for (uint32_t i = threadIdx.x; i < sv.coarse_words; i += blockDim.x) s_coarse[i] = __ldg(sv.coarse + i);
+	for (uint32_t i = threadIdx.x; i < sv.coarse_words; i += blockDim.x) s_coarse[i] = __ldg(sv.coarse + 2 * i);  // near words only
 	const uint32_t* coarse = s_coarse;
 	__syncthreads();
 	for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
@@ -561,6 +584,8 @@ struct bm_context {
 	bool use_quantum = true;  // BRICKMAP_B200_SIMPLE_KERNEL=1 switches the throughput path back to frame_kernel
 	int quantum = 64;         // BRICKMAP_B200_QUANTUM
 	int q_blocks = 0;
+	bool q_stock = false;
+	bool q_far = true;
 	size_t q_smem = 0;
 };
 
@@ -734,27 +759,30 @@ int bm_scene_bind(bm_context* c, bm_gpu_scene scene) {
 	sv.lod2 = c->cfg.lod_distance_2x2x2;
 	sv.lod8 = c->cfg.lod_distance_8x8x8;
 	sv.queue_size = (uint32_t)c->cfg.brick_load_queue_size;
-	// emptiness bitmap: the finest block size whose bitmap (rows padded to a power-of-two number of words) fits in 64 KiB of
-	// shared memory
-	int shift = 0, wshift = 0;
-	uint64_t words;
+	// emptiness bitmap: the finest block size whose bitmap (with its one-block border) fits in 64 KiB of shared memory
+	int shift = 0;
+	uint64_t words, roww, nby;
 	for (;; shift++) {
-		const uint64_t nb = (uint64_t)(sv.cells + (1 << shift) - 1) >> shift, nz = (uint64_t)(sv.cells_height + (1 << shift) - 1) >> shift;
-		for (wshift = 0; (32ull << wshift) < nb; wshift++) {}
-		words = (nz * nb) << wshift;
+		const uint64_t nb = ((uint64_t)(sv.cells + (1 << shift) - 1) >> shift) + 2, nz = ((uint64_t)(sv.cells_height + (1 << shift) - 1) >> shift) + 2;
+		roww = (nb + 31) / 32;
+		nby = nb;
+		words = nz * nb * roww;
 		if (words * 4 <= 64u * 1024u) break;
 	}
 	sv.coarse_shift = shift;
-	sv.coarse_nby = (sv.cells + (1 << shift) - 1) >> shift;
-	sv.coarse_wshift = wshift;
+	sv.coarse_nby = (int)nby;
+	sv.coarse_roww = (int)roww;
 	sv.coarse_words = (uint32_t)words;
 	cudaFree(c->d_coarse);
 	c->d_coarse = nullptr;
-	CK(cudaMalloc(&c->d_coarse, (size_t)sv.coarse_words * 4));
+	CK(cudaMalloc(&c->d_coarse, (size_t)sv.coarse_words * 8));  // {near, far} pairs
 	sv.coarse = nullptr;
 	sv.flat_indices = nullptr;
 	coarse_build_kernel<<<(sv.coarse_words * 32 + 255) / 256, 256, 0, c->stream>>>(sv, c->d_coarse);
 	CK(cudaGetLastError());
+	far_build_kernel<<<(sv.coarse_words * 32 + 255) / 256, 256, 0, c->stream>>>(sv, c->d_coarse);
+	CK(cudaGetLastError());
+	c->launches += 1;
 	sv.fine = nullptr;
 	sv.fine_nx = (sv.cells + 3) >> 2;
 	sv.fine_nxy = sv.fine_nx * sv.fine_nx;
@@ -791,10 +819,16 @@ int bm_scene_bind(bm_context* c, bm_gpu_scene scene) {
 	c->frame_blocks = c->sm_count * per_sm;
 	if (const char* e = getenv("BRICKMAP_B200_SIMPLE_KERNEL")) c->use_quantum = e[0] != '1';
 	if (const char* e = getenv("BRICKMAP_B200_QUANTUM")) c->quantum = atoi(e) > 0 ? atoi(e) : c->quantum;
-	if (sv.cells > 1024 || sv.cells_height > 1024) c->use_quantum = false;  // queue entries pack a cell position into 3 x 10 bits
-	c->q_smem = (size_t)sv.coarse_words * 4 + (size_t)(kQBlock / 32) * E_WORDS * kQueueEntries * 4;
-	CK(cudaFuncSetAttribute(frame_kernel_q, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)c->q_smem));
-	CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, frame_kernel_q, kQBlock, c->q_smem));
+	if (sv.cells + (2 << shift) > 65535 || sv.cells_height + (2 << shift) > 4095) c->use_quantum = false;  // queue entries pack the biased cell position into 16 + 16 + 12 bits
+	c->q_smem = (size_t)sv.coarse_words * 8 + (size_t)(kQBlock / 32) * E_WORDS * kQueueEntries * 4;
+	c->q_stock = sv.coarse_shift == 2 && sv.coarse_nby == 130 && sv.coarse_roww == 5;  // the stock world's bitmap geometry is compiled in
+	if (const char* e = getenv("BRICKMAP_B200_NO_FAR")) c->q_far = e[0] != '1';        // A/B switches for profiling
+	if (const char* e = getenv("BRICKMAP_B200_NO_STOCK")) c->q_stock = c->q_stock && e[0] != '1';
+	CK(cudaFuncSetAttribute(frame_kernel_q<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)c->q_smem));
+	CK(cudaFuncSetAttribute(frame_kernel_q<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)c->q_smem));
+	CK(cudaFuncSetAttribute(frame_kernel_q<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)c->q_smem));
+	CK(cudaFuncSetAttribute(frame_kernel_q<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)c->q_smem));
+	CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, frame_kernel_q<false, true>, kQBlock, c->q_smem));
 	if (per_sm < 1) c->use_quantum = false;
 	c->q_blocks = c->sm_count * (per_sm < 1 ? 1 : per_sm);
 	c->bound = true;
@@ -947,7 +981,10 @@ static int launch_frame_kernels(bm_context* c, const FrameIO& io, bool count) {
 	}
 	if (count) frame_kernel<RECORD, true><<<blocks, kTile, c->frame_smem, c->stream>>>(c->fp, c->sv, io);
 	else if (RECORD || !c->use_quantum) frame_kernel<RECORD, false><<<blocks, kTile, c->frame_smem, c->stream>>>(c->fp, c->sv, io);
-	else frame_kernel_q<<<c->q_blocks, kQBlock, c->q_smem, c->stream>>>(c->fp, c->sv, io, c->quantum);
+	else if (c->q_stock && c->q_far) frame_kernel_q<true, true><<<c->q_blocks, kQBlock, c->q_smem, c->stream>>>(c->fp, c->sv, io, c->quantum);
+	else if (c->q_far) frame_kernel_q<false, true><<<c->q_blocks, kQBlock, c->q_smem, c->stream>>>(c->fp, c->sv, io, c->quantum);
+	else if (c->q_stock) frame_kernel_q<true, false><<<c->q_blocks, kQBlock, c->q_smem, c->stream>>>(c->fp, c->sv, io, c->quantum);
+	else frame_kernel_q<false, false><<<c->q_blocks, kQBlock, c->q_smem, c->stream>>>(c->fp, c->sv, io, c->quantum);
 	CK(cudaGetLastError());
 	if (c->timing) CK(cudaEventRecord(e1, c->stream));
 	// the mask that was this frame's input becomes the next frame's output: the scan clears it

@@ -193,7 +193,7 @@ def test_fused_render_matches_oracle_over_many_frames(oracle, golden, stores):
     assert_records_equal(state.rays("next", c.primary_ray_cnt), oren.rays[: c.primary_ray_cnt], what="survivors after mixing both entry points")
 
 
-@pytest.mark.parametrize("variant", ["256", "256lod"])
+@pytest.mark.parametrize("variant", ["256", "256lod", "4096"])
 def test_throughput_kernel_matches_simple_kernel_on_adversarial_rays(golden, stores, variant):
     """The throughput path (bm_import_rays -> bm_render -> bm_export_rays, private sparse survivor storage) against the
     reference-layout path (bm_launch_frame on caller queues) on the same injected rays: exact ties between axes (diagonal and
@@ -240,6 +240,37 @@ def test_throughput_kernel_matches_simple_kernel_on_adversarial_rays(golden, sto
     assert [cf.primary_ray_cnt, cf.start_position, cf.frame] == [cs.primary_ray_cnt, cs.start_position, cs.frame]
     assert 0 < cf.primary_ray_cnt < n
     assert_records_equal(fast.export_rays(), want, what="survivors, bm_render vs bm_launch_frame")
+    a, b = blit.cpu().numpy(), state.blit_buffer.cpu().numpy()
+    assert np.array_equal(a[..., 3], b[..., 3])
+    assert_close_rel(a, b, 1e-5, "accumulation, bm_render vs bm_launch_frame")
+    sf, ss = fast.stats(), simple.stats()
+    assert [sf[k] for k in ("shadow_rays", "terminations", "unoccluded")] == [ss[k] for k in ("shadow_rays", "terminations", "unoccluded")]
+
+
+def test_throughput_kernel_matches_simple_kernel_on_the_stock_world(golden, stores):
+    """Three frames of the benchmark view on the 4096 x 4096 x 512 world: the throughput kernel (compiled-in bitmap geometry,
+    far-block runs of five DDA steps, suspend / resume through the per-warp queues) against the per-slot kernel behind
+    bm_launch_frame, which tests every cell. Survivor records bit for bit, alpha exactly, radiance to 1e-5."""
+    g = golden("4096")
+    store = stores("4096")
+    cfg = store.cfg
+    h, w = cfg.screen_height, cfg.screen_width
+    simple = renderer_for(g, store)
+    state = bm.State(cfg)
+    frames = 3
+    for f in range(frames):
+        simple.launch_kernels(state)
+        if f + 1 < frames:
+            state.swap()
+    cs = simple.counters()
+    want = state.rays("next", cs.primary_ray_cnt)
+
+    fast = renderer_for(g, store)
+    blit = torch.zeros(h, w, 4, dtype=torch.float32, device="cuda")
+    fast.render(blit, frames)
+    cf = fast.counters()
+    assert [cf.primary_ray_cnt, cf.start_position, cf.frame] == [cs.primary_ray_cnt, cs.start_position, cs.frame]
+    assert_records_equal(fast.export_rays(), want, what="survivors after %d frames, bm_render vs bm_launch_frame" % frames)
     a, b = blit.cpu().numpy(), state.blit_buffer.cpu().numpy()
     assert np.array_equal(a[..., 3], b[..., 3])
     assert_close_rel(a, b, 1e-5, "accumulation, bm_render vs bm_launch_frame")

@@ -45,14 +45,22 @@ print("total warp-instructions %d, samples %d" % (ti, ts))
 for k, v in sorted(agg.items(), key=lambda kv: -kv[1][0])[:top]:
     print("%-16s %4d inst=%5.1f%% lanes=%5.1f smp=%5.1f%% | %s" % (k[0][:16], k[1], 100 * v[0] / max(ti, 1), v[1] / max(v[0], 1), 100 * v[2] / max(ts, 1), v[3].strip()))
 
-# ---- per-region totals (line ranges of the current sources; adjust when the files change) --------------------------------
-regions = {
-    "bm_frame_v2.cuh": [(81, 106, "classify_cell"), (107, 150, "jump_advance"), (151, 174, "sub test/hit"), (175, 213, "trace_begin"), (214, 243, "trace_descend"),
-                        (244, 288, "kernel prologue + scheduler"), (289, 371, "SHADE+REFILL section"), (372, 426, "CELL section"), (427, 470, "TRACE loop"), (471, 999, "epilogue")],
-    "bm_device.cuh": [(1, 84, "math/rng helpers"), (139, 151, "dda_setup"), (221, 232, "aabb"), (324, 372, "sky"), (373, 398, "cone/basis"), (407, 441, "generate_primary"),
-                      (450, 495, "shade_vertex"), (496, 530, "load/store ray")],
-    "bm_kernels.cu": [(1, 9999, "bm_kernels.cu (survivor_ptr, accum)")],
-}
+# ---- per-region totals: regions = the __device__/__global__ functions of the current sources (start line .. next start), and the
+#      "// ---- " sections inside the quantum kernel
+import os
+import re
+CSRC = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "brickmap_b200", "csrc")
+regions = {}
+for fn in os.listdir(CSRC):
+    starts = []
+    for n, line in enumerate(open(os.path.join(CSRC, fn)), 1):
+        m = re.match(r"^(?:__device__|__global__|static|template).*?(\w+)\s*\(", line)
+        if m and not line.startswith("template <"):
+            starts.append((n, m.group(1)))
+        m = re.match(r"^\s*// ---- (.*?) -*$", line)
+        if m and fn == "bm_frame_quantum.cuh":
+            starts.append((n, "q: " + m.group(1).strip()[:40]))
+    regions[fn] = [(a, (starts[k + 1][0] - 1) if k + 1 < len(starts) else 99999, nm) for k, (a, nm) in enumerate(starts)]
 tot = collections.defaultdict(lambda: [0, 0, 0])
 for (f, ln), v in agg.items():
     name = f + " other"
