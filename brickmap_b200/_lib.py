@@ -4,7 +4,7 @@ import ctypes as C
 import os
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(HERE, "libbrickmap_b200.so")
+LIB_PATH = os.environ.get("BRICKMAP_B200_LIB") or os.path.join(HERE, "libbrickmap_b200.so")  # the override is for A/B builds of the same sources
 
 
 class Config(C.Structure):  # bm_config

@@ -120,9 +120,9 @@ struct SceneView {
 	                              // For a cell position p biased by one block (p' = p + (1 << coarse_shift)), b = p' >> coarse_shift:
 	                              // bit (b.x & 31) of word (b.z * coarse_nby + b.y) * coarse_roww + (b.x >> 5). The one cell a DDA can
 	                              // stand in outside the world falls into the border, so the empty-space loop needs no bounds test.
-	                              // Stored as PAIRS of words {near, far}: near = the bitmap above; far bit set iff the block and its 26
-	                              // neighbours are all empty (never for border blocks), i.e. every cell within Chebyshev distance 4 of
-	                              // any cell of the block is empty and inside the world
+	                              // Stored as PAIRS of words {near, far}: near = the bitmap above. far bit, where near is clear: the block and
+	                              // its 26 neighbours are all empty and inside the world, i.e. so is every cell within Chebyshev distance
+	                              // (block width) of any cell of the block. far bit, where near is set: the block is a BORDER block
 	int cells, cells_height;      // variables.h:17-18
 	int supergrid_xy;             // variables.h:12
 	float grid_size_f, grid_height_f;
@@ -287,15 +287,24 @@ __device__ __forceinline__ bool intersect_brick(const F3& origin, const F3& dire
 	Dda a;
 	dda_setup_nested(origin, direction, parent, a);
 	const I3 lim{ 8, 8, 8 };
-	a.pos = I3{ a.pos.x % 8, a.pos.y % 8, a.pos.z % 8 };
+	// The remainders cannot be negative: origin = 8 x - n eps with x inside a cell of the world, so every component is > -1 and
+	// truncates to >= 0 (the reference would index out of the brick otherwise, voxel.cuh:103,110-113); & 7 == % 8 then.
+	a.pos = I3{ a.pos.x & 7, a.pos.y & 7, a.pos.z & 7 };
 	distance = 0.f;
 	int step_axis = -1;
 	const uint32_t* words = brick->data;
 	for (;;) {
 		const int lin = a.pos.x + a.pos.y * 8 + a.pos.z * 64;
-		// negative remainders (origin slightly outside on the low side) index out of the brick in the reference
-		// (undefined there); they are treated as empty here and in the oracle
-		if (lin >= 0 && lin < 512 && ((__ldg(words + (lin >> 5)) >> (lin & 31)) & 1u)) {
+		const uint32_t w = __ldg(words + (lin >> 5));
+		uint32_t set;
+		asm("{\n\t"
+		    ".reg .b32 m;\n\t"
+		    "shf.l.wrap.b32 m, 0, 1, %1;\n\t"
+		    "and.b32 %0, %2, m;\n\t"
+		    "}"
+		    : "=r"(set)
+		    : "r"(lin), "r"(w));
+		if (set) {
 			if (step_axis > -1) {
 				normal = axis_normal(a, step_axis);
 				distance = comp(a.tmax, step_axis) - comp(a.tdelta, step_axis);
@@ -356,6 +365,10 @@ __device__ __forceinline__ bool trace_setup(const SceneView& sv, F3 origin, cons
 }
 
 enum : int { TRACE_MISS = 0, TRACE_HIT = 1, TRACE_SUSPENDED = 2 };
+#ifndef BM_TRACE_CHUNK
+#define BM_TRACE_CHUNK 8
+#endif
+constexpr int kTraceChunk = BM_TRACE_CHUNK;  // cell tests between two looks at the budget (and, deferred bricks: between two brick walks)
 
 // The DDA loop of intersect_voxel (voxel.cuh:192-259). `coarse_smem` is the block's shared-memory copy of the emptiness
 // bitmap. The DDA performs exactly the reference's sequence of floating-point steps; only the LOADS of index words for empty
@@ -371,7 +384,7 @@ enum : int { TRACE_MISS = 0, TRACE_HIT = 1, TRACE_SUSPENDED = 2 };
 // per slab) as compile-time constants.
 template <bool COUNT, bool BOUNDED, bool FAR = false, bool STOCK = false>
 __device__ __forceinline__ int trace_run(const SceneView& sv, const uint32_t* coarse_smem, const F3 direction, F3& normal, float& distance, const I3 cam,
-                                         TraceState& ts, int budget, WorkCounters* wc) {
+                                         TraceState& ts, int budget, WorkCounters* wc, int min_lanes = 0) {
 	const F3 origin = ts.origin;
 	const float tminn = ts.tminn;
 	Dda& a = ts.a;
@@ -383,8 +396,12 @@ __device__ __forceinline__ int trace_run(const SceneView& sv, const uint32_t* co
 	uint32_t smem_base = (uint32_t)__cvta_generic_to_shared(bm_dyn_smem);  // shared-window address of the bitmap ...
 	asm volatile("" : "+r"(smem_base));  // ... pinned in a register (left alone the compiler re-derives it in every step)
 
-	bool left_world = false;
-	for (int it = budget; !BOUNDED || it > 0; it--) {
+	// The loop runs in chunks of kTraceChunk cell tests. BOUNDED: after each chunk the ray is suspended if its budget is used up
+	// or if fewer than `min_lanes` lanes of the warp are still tracing (the others have finished their rays and wait): the caller
+	// puts suspended rays into its queue and resumes them 32 at a time, so a thin warp is better given up early. Which lanes
+	// are "still here" is read with __activemask(): a heuristic only, suspending never changes a result.
+	for (int it = budget;;) {
+	for (int chunk = kTraceChunk; chunk > 0; chunk--) {
 		// Is the cell possibly non-empty? Shared-memory bitmap over blocks of cells first, then one bit per cell (global).
 		if (COUNT) wc->steps++;
 		const int bx = a.pos.x >> shift;
@@ -404,10 +421,11 @@ __device__ __forceinline__ int trace_run(const SceneView& sv, const uint32_t* co
 		const bool far = FAR && !COUNT && far_bit;
 		if (near_bit) {
 			const I3 p{ a.pos.x - bias, a.pos.y - bias, a.pos.z - bias };
-			if ((unsigned)p.x >= (unsigned)sv.cells || (unsigned)p.y >= (unsigned)sv.cells || (unsigned)p.z >= (unsigned)sv.cells_height) {  // voxel.cuh:256
+			// outside the world? With the far words at hand that is one more bit test: border blocks have BOTH bits set
+			if (FAR ? far_bit != 0u
+			        : ((unsigned)p.x >= (unsigned)sv.cells || (unsigned)p.y >= (unsigned)sv.cells || (unsigned)p.z >= (unsigned)sv.cells_height)) {  // voxel.cuh:256
 				if (COUNT) wc->steps--;  // not a cell test of the reference: its loop ended with the step that left the world
-				left_world = true;
-				break;
+				return TRACE_MISS;
 			}
 			const int fb = (p.x >> 2) + (p.y >> 2) * sv.fine_nx + (p.z >> 2) * sv.fine_nxy;
 			const int fbit = (p.x & 3) | ((p.y & 3) << 2) | ((p.z & 3) << 4);
@@ -415,6 +433,9 @@ __device__ __forceinline__ int trace_run(const SceneView& sv, const uint32_t* co
 				const int sc = (p.x >> 4) + (p.y >> 4) * sv.supergrid_xy + (p.z >> 4) * sv.supergrid_xy * sv.supergrid_xy;  // voxel.cuh:197
 				const int local = (p.x & 15) + (p.y & 15) * 16 + (p.z & 15) * 256;                                        // voxel.cuh:198
 				uint32_t* word = sv.flat_indices ? sv.flat_indices + (((size_t)sc << 12) + local) : sv.indices[sc] + local;
+				// the per-cell bit is set iff the index word is non-zero: what the word will be needed for can start now, the
+				// brick-table entry is loaded alongside the word instead of after it
+				const bm_brick* const bricks_sc = sv.bricks[sc];
 				const uint32_t index = __ldg(word);
 				if (COUNT) wc->index_reads++;
 				if (index) {
@@ -437,7 +458,10 @@ __device__ __forceinline__ int trace_run(const SceneView& sv, const uint32_t* co
 								return TRACE_HIT;
 						}
 					} else if (index & BM_BRICK_LOADED_BIT) {  // voxel.cuh:222-227
-						const bm_brick* b = sv.bricks[sc] + (index & BM_BRICK_INDEX_BITS);
+						const bm_brick* b = bricks_sc + (index & BM_BRICK_INDEX_BITS);
+						// both 32-byte halves of the brick on their way while the sub-DDA is set up (its loads are one word per step)
+						asm volatile("prefetch.global.L1 [%0];" ::"l"(b));
+						asm volatile("prefetch.global.L1 [%0];" ::"l"(reinterpret_cast<const char*>(b) + 32));
 						if (COUNT) wc->bricks++;
 						const F3 x{ fmaf(direction.x, new_distance, origin.x), fmaf(direction.y, new_distance, origin.y), fmaf(direction.z, new_distance, origin.z) };
 						const F3 so{ x.x * 8.f - normal.x * kEpsilon, x.y * 8.f - normal.y * kEpsilon, x.z * 8.f - normal.z * kEpsilon };
@@ -477,9 +501,155 @@ __device__ __forceinline__ int trace_run(const SceneView& sv, const uint32_t* co
 		}
 		dda_step(a, step_axis);
 	}
-	return (BOUNDED && !left_world) ? TRACE_SUSPENDED : TRACE_MISS;
+		if (BOUNDED) {
+			it -= kTraceChunk;
+			if (it <= 0 || __popc(__activemask()) < min_lanes) return TRACE_SUSPENDED;
+		}
+	}
 }
 
+
+// trace_run with DEFERRED BRICKS (throughput kernel). In trace_run a lane that reaches a loaded brick walks its 8^3 voxels on
+// the spot while the rest of the warp waits: a quarter of all issued instructions run with 6 of 32 lanes. Four out of five
+// bricks a ray enters are missed, so here the lane only notes the brick down (pointer, entry distance, entry axis: a "job" in
+// shared memory) and steps on as if it had missed. At the end of every chunk of kTraceChunk cell tests the lanes of the warp
+// walk their noted bricks TOGETHER, in the order they were met. A hit ends the ray there -- what the lane did after that
+// brick is dropped, which is exact: the steps past a missed brick are the steps the reference takes, and nothing with a
+// side effect (brick request, LoD hit, leaving the world) is acted on while a job is pending: the lane stops in front of it
+// and looks at that cell again once its bricks are resolved. `normal` is not touched by a noted brick that is missed; the
+// reference overwrites it there (voxel.cuh:203), but any later hit overwrites it again and a miss does not use it.
+constexpr int kJobs = 2;  // noted bricks per lane and chunk
+template <bool STOCK>
+__device__ __forceinline__ int trace_run_deferred(const SceneView& sv, const F3 direction, F3& normal, float& distance, const I3 cam, TraceState& ts, int budget,
+                                                  int min_lanes, uint32_t* jobs /* this lane's column of the warp's job area: word (j * 4 + f) * 32 */) {
+	const F3 origin = ts.origin;
+	const float tminn = ts.tminn;
+	Dda& a = ts.a;
+	int& step_axis = ts.step_axis;
+	const int shift = STOCK ? 2 : sv.coarse_shift;
+	const int nby = STOCK ? 130 : sv.coarse_nby, roww = STOCK ? 5 : sv.coarse_roww;
+	const int bias = 1 << shift;
+	uint32_t smem_base = (uint32_t)__cvta_generic_to_shared(bm_dyn_smem);
+	asm volatile("" : "+r"(smem_base));
+
+	int njobs = 0;
+	bool left_world = false;
+	for (int it = budget;;) {
+		for (int chunk = kTraceChunk; chunk > 0; chunk--) {
+			const int bx = a.pos.x >> shift;
+			const int w = ((a.pos.z >> shift) * nby + (a.pos.y >> shift)) * roww + (bx >> 5);
+			uint32_t cw;
+			asm("ld.shared.u32 %0, [%1];" : "=r"(cw) : "r"(smem_base + (w << 2)));
+			uint32_t near_bit;
+			asm("{\n\t"
+			    ".reg .b32 m;\n\t"
+			    "shf.l.wrap.b32 m, 0, 1, %1;\n\t"
+			    "and.b32 %0, %2, m;\n\t"
+			    "}"
+			    : "=r"(near_bit)
+			    : "r"(bx), "r"(cw));
+			if (near_bit) {
+				const I3 p{ a.pos.x - bias, a.pos.y - bias, a.pos.z - bias };
+				if ((unsigned)p.x >= (unsigned)sv.cells || (unsigned)p.y >= (unsigned)sv.cells || (unsigned)p.z >= (unsigned)sv.cells_height) {  // voxel.cuh:256
+					if (njobs == 0) return TRACE_MISS;
+					left_world = true;  // a miss unless one of the noted bricks is hit
+					break;
+				}
+				const int fb = (p.x >> 2) + (p.y >> 2) * sv.fine_nx + (p.z >> 2) * sv.fine_nxy;
+				const int fbit = (p.x & 3) | ((p.y & 3) << 2) | ((p.z & 3) << 4);
+				if ((__ldg(sv.fine + (size_t)fb * 2 + (fbit >> 5)) >> (fbit & 31)) & 1u) {
+					const int sc = (p.x >> 4) + (p.y >> 4) * sv.supergrid_xy + (p.z >> 4) * sv.supergrid_xy * sv.supergrid_xy;  // voxel.cuh:197
+					const int local = (p.x & 15) + (p.y & 15) * 16 + (p.z & 15) * 256;                                        // voxel.cuh:198
+					uint32_t* word = sv.flat_indices ? sv.flat_indices + (((size_t)sc << 12) + local) : sv.indices[sc] + local;
+					const bm_brick* const bricks_sc = sv.bricks[sc];
+					const uint32_t index = __ldg(word);
+					if (index) {
+						const int dx = cam.x - p.x, dy = cam.y - p.y, dz = cam.z - p.z;
+						const int lod_distance_squared = dx * dx + dy * dy + dz * dz;
+						const bool is_brick = !(lod_distance_squared > sv.lod8) && !(lod_distance_squared > sv.lod2) && (index & BM_BRICK_LOADED_BIT);  // voxel.cuh:212-222
+						if (is_brick && njobs < kJobs) {
+							const bm_brick* b = bricks_sc + (index & BM_BRICK_INDEX_BITS);
+							asm volatile("prefetch.global.L1 [%0];" ::"l"(b));
+							asm volatile("prefetch.global.L1 [%0];" ::"l"(reinterpret_cast<const char*>(b) + 32));
+							const float new_distance = step_axis != -1 ? comp(a.tmax, step_axis) - comp(a.tdelta, step_axis) : 0.f;
+							uint32_t* job = jobs + njobs * (4 * 32);
+							job[0] = (uint32_t)(uintptr_t)b;
+							job[32] = (uint32_t)((uintptr_t)b >> 32);
+							job[64] = __float_as_uint(new_distance);
+							job[96] = (uint32_t)(step_axis + 1);
+							njobs++;
+						} else if (njobs) {
+							break;  // stop in front of this cell; it is looked at again once the noted bricks are resolved
+						} else {
+							float new_distance = 0.f;
+							if (step_axis != -1) {
+								normal = axis_normal(a, step_axis);
+								new_distance = comp(a.tmax, step_axis) - comp(a.tdelta, step_axis);
+							}
+							float sub_distance = 0.f;
+							if (lod_distance_squared > sv.lod8) {  // voxel.cuh:212-214
+								distance = new_distance * 8.f + tminn;
+								return TRACE_HIT;
+							} else if (lod_distance_squared > sv.lod2) {  // voxel.cuh:215-220
+								const F3 x{ fmaf(direction.x, new_distance, origin.x), fmaf(direction.y, new_distance, origin.y), fmaf(direction.z, new_distance, origin.z) };
+								const F3 so{ fmaf(normal.x * 0.2f, -kEpsilon, x.x + x.x), fmaf(normal.y * 0.2f, -kEpsilon, x.y + x.y), fmaf(normal.z * 0.2f, -kEpsilon, x.z + x.z) };
+								if (intersect_byte(so, direction, a, normal, sub_distance, (index & BM_BRICK_LOD_BITS) >> 12)) {
+									distance = (new_distance * 8.f + sub_distance * 4.f) + tminn;
+									return TRACE_HIT;
+								}
+							} else if (index & BM_BRICK_LOADED_BIT) {  // only with kJobs == 0
+								const bm_brick* b = bricks_sc + (index & BM_BRICK_INDEX_BITS);
+								const F3 x{ fmaf(direction.x, new_distance, origin.x), fmaf(direction.y, new_distance, origin.y), fmaf(direction.z, new_distance, origin.z) };
+								const F3 so{ x.x * 8.f - normal.x * kEpsilon, x.y * 8.f - normal.y * kEpsilon, x.z * 8.f - normal.z * kEpsilon };
+								if (intersect_brick(so, direction, a, normal, sub_distance, b)) {
+									distance = (new_distance * 8.f + sub_distance) + tminn;
+									return TRACE_HIT;
+								}
+							} else if (index & BM_BRICK_UNLOADED_BIT) {  // voxel.cuh:228-244
+								const uint32_t old = atomicOr(word, BM_BRICK_REQUESTED_BIT);
+								if (!(old & BM_BRICK_REQUESTED_BIT)) {
+									const uint32_t load_index = atomicAdd(sv.load_queue_count, 1u);
+									if (load_index < sv.queue_size) {
+										sv.load_queue[3 * load_index + 0] = p.x;
+										sv.load_queue[3 * load_index + 1] = p.y;
+										sv.load_queue[3 * load_index + 2] = p.z;
+									} else {
+										atomicAnd(word, ~BM_BRICK_REQUESTED_BIT);
+									}
+								}
+								distance = new_distance * 8.f + tminn;
+								return TRACE_HIT;
+							}
+						}
+					}
+				}
+			}
+			dda_step(a, step_axis);
+		}
+		// ---- the warp's noted bricks, walked together (voxel.cuh:222-227), in the order each lane met them
+#pragma unroll 1
+		for (int j = 0; j < njobs; j++) {
+			const uint32_t* job = jobs + j * (4 * 32);
+			const bm_brick* b = reinterpret_cast<const bm_brick*>((uintptr_t)job[0] | ((uintptr_t)job[32] << 32));
+			const float new_distance = __uint_as_float(job[64]);
+			const int axis = (int)job[96] - 1;
+			F3 n = normal;
+			if (axis != -1) n = axis_normal(a, axis);
+			const F3 x{ fmaf(direction.x, new_distance, origin.x), fmaf(direction.y, new_distance, origin.y), fmaf(direction.z, new_distance, origin.z) };
+			const F3 so{ x.x * 8.f - n.x * kEpsilon, x.y * 8.f - n.y * kEpsilon, x.z * 8.f - n.z * kEpsilon };
+			float sub_distance = 0.f;
+			if (intersect_brick(so, direction, a, n, sub_distance, b)) {
+				normal = n;
+				distance = (new_distance * 8.f + sub_distance) + tminn;
+				return TRACE_HIT;
+			}
+		}
+		njobs = 0;
+		if (left_world) return TRACE_MISS;
+		it -= kTraceChunk;
+		if (it <= 0 || __popc(__activemask()) < min_lanes) return TRACE_SUSPENDED;
+	}
+}
 
 // intersect_voxel, voxel.cuh:135-261
 template <bool COUNT>

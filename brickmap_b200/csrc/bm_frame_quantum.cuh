@@ -9,22 +9,28 @@
 // quantum of 64 and 86 % at 32. Shadow rays go through the same queue (they are born into it by shade), so they too are
 // traced 32 at a time and in quanta. Suspending never changes a result: the DDA state is saved and restored exactly.
 //
-// One queue entry = 20 words, structure of arrays per warp, 64 entries (a batch pops at most 32 and every lane pushes at most
+// Only rays that start inside the world (tminn == 0, voxel.cuh:136-141) are ever suspended: for them the trace-space origin is
+// the world-space origin times 1/8 exactly, so the entry needs neither tminn nor the world-space origin that shading wants. A
+// ray that enters from outside gets an unbounded quantum (all primaries of an outside camera: the kernel then behaves like
+// frame_kernel for them).
+// One queue entry = 16 words, structure of arrays per warp, 64 entries (a batch pops at most 32 and every lane pushes at most
 // one entry per batch: the ray it had to suspend, or the shadow ray its shaded vertex produced).
 #pragma once
 
 namespace bm {
 
-constexpr int kQBlock = 768;       // 24 warps, one block per SM (shared memory: near/far bitmap pairs 92 KiB + 24 queues 120 KiB)
+#ifndef BM_QBLOCK
+#define BM_QBLOCK 1024
+#endif
+constexpr int kQBlock = BM_QBLOCK;  // 32 warps, one block per SM (shared memory: bitmap 46 KiB [92 KiB with the far words] + 32 queues 128 KiB).
+                                    // Measured on the benchmark view: 512 threads 2.06, 768 2.35, 1024 2.49 Grays/s
 constexpr int kQueueEntries = 64;
 enum : int {
 	E_OX = 0, E_OY, E_OZ,   // trace-space origin in cell units (continuations) / world-space origin (new shadow rays)
 	E_DX, E_DY, E_DZ,       // direction
 	E_POS,                  // (biased) cell position x | y << 16; z is in E_FLAGS
 	E_TX, E_TY, E_TZ,       // tmax
-	E_TMIN,                 // tminn
 	E_FLAGS,                // kind | (last stepped axis + 1) << 2 | cell position z << 4 (12 bits) | bounces << 16
-	E_WX, E_WY, E_WZ,       // world-space origin of an extend ray (shading needs it)
 	E_CX, E_CY, E_CZ,       // throughput of an extend ray / colour of a shadow ray
 	E_PIXEL, E_SLOT,
 	E_WORDS
@@ -34,11 +40,14 @@ enum : int { K_NONE = -1, K_EXTEND = 0, K_SHADOW = 1, K_SHADOW_NEW = 2 };
 #define QF(field, e) q[(field) * kQueueEntries + (e)]
 #define QU(field, e) reinterpret_cast<uint32_t*>(q)[(field) * kQueueEntries + (e)]
 
-template <bool STOCK, bool FAR>
-__global__ void __launch_bounds__(kQBlock, 1) frame_kernel_q(const FrameParams fp, const SceneView sv, const FrameIO io, const int quantum) {
+// MODE: 0 = trace_run, 1 = trace_run with the far words (five-step runs), 2 = trace_run_deferred (bricks noted and walked together)
+enum : int { Q_PLAIN = 0, Q_FAR = 1, Q_DEFERRED = 2 };
+template <bool STOCK, int MODE>
+__global__ void __launch_bounds__(kQBlock, 1) frame_kernel_q(const FrameParams fp, const SceneView sv, const FrameIO io, const int quantum, const int min_share, const int descending) {
 	extern __shared__ uint32_t s_coarse[];
 	DeviceState* st = io.st;
 	if (st->done) return;
+	constexpr bool FAR = MODE == Q_FAR;
 	if (FAR) for (uint32_t i = threadIdx.x; i < 2 * sv.coarse_words; i += blockDim.x) s_coarse[i] = __ldg(sv.coarse + i);  // {near, far} pairs
 	else for (uint32_t i = threadIdx.x; i < sv.coarse_words; i += blockDim.x) s_coarse[i] = __ldg(sv.coarse + 2 * i);    // near words only
 	const uint32_t* coarse = s_coarse;
@@ -49,7 +58,10 @@ __global__ void __launch_bounds__(kQBlock, 1) frame_kernel_q(const FrameParams f
 	const uint32_t frame = st->frame;
 	const uint32_t lane = threadIdx.x & 31;
 	const uint32_t lt_mask = (1u << lane) - 1u;
-	float* q = reinterpret_cast<float*>(s_coarse + 2 * sv.coarse_words) + (threadIdx.x >> 5) * (E_WORDS * kQueueEntries);
+	float* q = reinterpret_cast<float*>(s_coarse + (FAR ? 2 : 1) * sv.coarse_words) + (threadIdx.x >> 5) * (E_WORDS * kQueueEntries);
+	// Q_DEFERRED: the warp's brick jobs behind all queues, kJobs x 4 words per lane, lane-interleaved
+	uint32_t* jobs = reinterpret_cast<uint32_t*>(s_coarse + (FAR ? 2 : 1) * sv.coarse_words) + (kQBlock / 32) * (E_WORDS * kQueueEntries) +
+	                 (threadIdx.x >> 5) * (kJobs * 4 * 32) + lane;
 	uint32_t qn = 0;  // entries in the warp's queue (warp-uniform)
 	uint32_t n_shadow = 0, n_term = 0, n_unocc = 0;
 
@@ -86,12 +98,12 @@ __global__ void __launch_bounds__(kQBlock, 1) frame_kernel_q(const FrameParams f
 					tracing = trace_setup(sv, F3{ QF(E_OX, e), QF(E_OY, e), QF(E_OZ, e) }, direction, normal, ts);
 				} else {
 					if (kind == K_EXTEND) {
-						world = F3{ QF(E_WX, e), QF(E_WY, e), QF(E_WZ, e) };
 						slot = QU(E_SLOT, e);
 					}
 					// the traversal state exactly as it was saved; tdelta and the integer steps as dda_setup derives them
 					ts.origin = F3{ QF(E_OX, e), QF(E_OY, e), QF(E_OZ, e) };
-					ts.tminn = QF(E_TMIN, e);
+					ts.tminn = 0.f;
+					world = F3{ ts.origin.x * 8.f, ts.origin.y * 8.f, ts.origin.z * 8.f };  // exact inverse of trace_setup's origin / 8
 					const uint32_t packed = QU(E_POS, e);
 					ts.a.pos = I3{ (int)(packed & 0xFFFFu), (int)(packed >> 16), (int)((flags >> 4) & 0xFFFu) };
 					ts.step_axis = (int)((flags >> 2) & 3u) - 1;
@@ -114,6 +126,9 @@ __global__ void __launch_bounds__(kQBlock, 1) frame_kernel_q(const FrameParams f
 					pool_dry = true;
 					continue;
 				}
+				// Which slots a warp takes when is free (results are per slot). Descending = the frame's fresh primary rays before
+				// the survivors of the previous frame: the longest rays (primaries near the horizon) start first, the tail shrinks.
+				if (descending) run = nruns - 1 - run;
 			}
 			slot = (run * kRun + round) * 32 + lane;
 			round++;
@@ -137,7 +152,16 @@ __global__ void __launch_bounds__(kQBlock, 1) frame_kernel_q(const FrameParams f
 
 		// ---- one quantum of traversal -------------------------------------------------------------------------------------
 		WorkCounters wc;
-		if (tracing) status = trace_run<false, true, FAR, STOCK>(sv, coarse, direction, normal, distance, fp.cam_cell, ts, quantum, &wc);
+		// give the batch up (suspend what is left of it) once fewer than min_share / 32 of the lanes that started tracing are
+		// still at it; rays that entered the world from outside cannot be suspended (see above) and run to their end
+		const int min_lanes = (__popc(__ballot_sync(0xFFFFFFFFu, tracing)) * min_share) >> 5;
+		if (tracing) {
+			const bool pinned = ts.tminn > 0.f;
+			if (MODE == Q_DEFERRED)
+				status = trace_run_deferred<STOCK>(sv, direction, normal, distance, fp.cam_cell, ts, pinned ? 0x3FFFFFF8 : quantum, pinned ? 0 : min_lanes, jobs);
+			else
+				status = trace_run<false, true, FAR, STOCK>(sv, coarse, direction, normal, distance, fp.cam_cell, ts, pinned ? 0x3FFFFFF8 : quantum, &wc, pinned ? 0 : min_lanes);
+		}
 		__syncwarp();  // lanes whose ray ended early wait here: they are shaded together, not interleaved with the tracing lanes
 
 		// ---- outcomes -----------------------------------------------------------------------------------------------------
@@ -205,14 +229,10 @@ __global__ void __launch_bounds__(kQBlock, 1) frame_kernel_q(const FrameParams f
 				QF(E_DX, e) = direction.x; QF(E_DY, e) = direction.y; QF(E_DZ, e) = direction.z;
 				QU(E_POS, e) = (uint32_t)ts.a.pos.x | ((uint32_t)ts.a.pos.y << 16);
 				QF(E_TX, e) = ts.a.tmax.x; QF(E_TY, e) = ts.a.tmax.y; QF(E_TZ, e) = ts.a.tmax.z;
-				QF(E_TMIN, e) = ts.tminn;
 				QU(E_FLAGS, e) = (uint32_t)push | ((uint32_t)(ts.step_axis + 1) << 2) | ((uint32_t)ts.a.pos.z << 4) | ((uint32_t)bounces << 16);
 				QF(E_CX, e) = payload.x; QF(E_CY, e) = payload.y; QF(E_CZ, e) = payload.z;
 				QU(E_PIXEL, e) = pixel;
-				if (push == K_EXTEND) {
-					QF(E_WX, e) = world.x; QF(E_WY, e) = world.y; QF(E_WZ, e) = world.z;
-					QU(E_SLOT, e) = slot;
-				}
+				if (push == K_EXTEND) QU(E_SLOT, e) = slot;
 			}
 		}
 		qn += __popc(pm);

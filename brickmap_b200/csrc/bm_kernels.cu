@@ -440,14 +440,17 @@ __global__ void coarse_build_kernel(const SceneView sv, uint32_t* coarse) {
 	if (lane == 0) coarse[2 * word] = ballot;
 }
 
-// far words of the {near, far} pairs: block and its 26 neighbours all empty (SceneView::coarse). One thread per block bit.
+// far words of the {near, far} pairs (SceneView::coarse): block and its 26 neighbours all empty, or -- together with the near
+// bit -- border block. One thread per block bit.
 __global__ void far_build_kernel(const SceneView sv, uint32_t* coarse) {
 	const uint32_t gid = blockIdx.x * blockDim.x + threadIdx.x;
 	const uint32_t word = gid >> 5, lane = gid & 31;
 	if (word >= sv.coarse_words) return;
+	const int side = 1 << sv.coarse_shift;
 	const int nbx = sv.coarse_roww * 32, nby = sv.coarse_nby, nbz = (int)(sv.coarse_words / (uint32_t)(sv.coarse_roww * sv.coarse_nby));
 	const int row = word / sv.coarse_roww, bx = (int)((word % sv.coarse_roww) << 5) + (int)lane;
 	const int by = row % nby, bz = row / nby;
+	const bool border = bx < 1 || by < 1 || bz < 1 || (bx - 1) * side >= sv.cells || (by - 1) * side >= sv.cells || (bz - 1) * side >= sv.cells_height;
 	bool far = true;
 	for (int dz = -1; dz <= 1 && far; dz++)
 		for (int dy = -1; dy <= 1 && far; dy++)
@@ -457,7 +460,7 @@ __global__ void far_build_kernel(const SceneView sv, uint32_t* coarse) {
 				const uint32_t w = coarse[2 * ((size_t)(z * nby + y) * sv.coarse_roww + (x >> 5))];
 				if ((w >> (x & 31)) & 1u) { far = false; break; }
 			}
-	const uint32_t ballot = __ballot_sync(0xFFFFFFFFu, far);
+	const uint32_t ballot = __ballot_sync(0xFFFFFFFFu, far || border);
 	if (lane == 0) coarse[2 * word + 1] = ballot;
 }
 
@@ -582,12 +585,20 @@ struct bm_context {
 	size_t frame_smem = 0;
 	// throughput kernel (frame_kernel_q)
 	bool use_quantum = true;  // BRICKMAP_B200_SIMPLE_KERNEL=1 switches the throughput path back to frame_kernel
-	int quantum = 64;         // BRICKMAP_B200_QUANTUM
+	int quantum = 128;        // BRICKMAP_B200_QUANTUM (cell tests per lane and batch; 128 measured best on the benchmark view)
+	int min_share = 0;        // BRICKMAP_B200_MIN_SHARE: a batch is given up when fewer than min_share / 32 of its tracing lanes are left
+	int descending = 0;       // BRICKMAP_B200_DESCENDING: hand out slot runs from the end of the frame
 	int q_blocks = 0;
 	bool q_stock = false;
-	bool q_far = true;
+	int q_mode = 0;           // BRICKMAP_B200_MODE: Q_PLAIN / Q_FAR / Q_DEFERRED (bm_frame_quantum.cuh)
 	size_t q_smem = 0;
 };
+
+static int props_smem_optin(int device) {
+	int v = 0;
+	cudaDeviceGetAttribute(&v, cudaDevAttrMaxSharedMemoryPerBlockOptin, device);
+	return v;
+}
 
 static inline F3 h_cross(const F3& a, const F3& b) { return F3{ a.y * b.z - b.y * a.z, a.z * b.x - b.z * a.x, a.x * b.y - b.x * a.y }; }
 static inline F3 h_normalize(const F3& v) {
@@ -819,16 +830,28 @@ int bm_scene_bind(bm_context* c, bm_gpu_scene scene) {
 	c->frame_blocks = c->sm_count * per_sm;
 	if (const char* e = getenv("BRICKMAP_B200_SIMPLE_KERNEL")) c->use_quantum = e[0] != '1';
 	if (const char* e = getenv("BRICKMAP_B200_QUANTUM")) c->quantum = atoi(e) > 0 ? atoi(e) : c->quantum;
+	c->quantum = (c->quantum + kTraceChunk - 1) / kTraceChunk * kTraceChunk;
+	if (const char* e = getenv("BRICKMAP_B200_DESCENDING")) c->descending = e[0] == '1';
+	if (const char* e = getenv("BRICKMAP_B200_MIN_SHARE")) c->min_share = atoi(e) >= 0 && atoi(e) <= 32 ? atoi(e) : c->min_share;
 	if (sv.cells + (2 << shift) > 65535 || sv.cells_height + (2 << shift) > 4095) c->use_quantum = false;  // queue entries pack the biased cell position into 16 + 16 + 12 bits
-	c->q_smem = (size_t)sv.coarse_words * 8 + (size_t)(kQBlock / 32) * E_WORDS * kQueueEntries * 4;
 	c->q_stock = sv.coarse_shift == 2 && sv.coarse_nby == 130 && sv.coarse_roww == 5;  // the stock world's bitmap geometry is compiled in
-	if (const char* e = getenv("BRICKMAP_B200_NO_FAR")) c->q_far = e[0] != '1';        // A/B switches for profiling
+	if (const char* e = getenv("BRICKMAP_B200_MODE")) c->q_mode = atoi(e) >= 0 && atoi(e) <= 2 ? atoi(e) : c->q_mode;  // A/B switches for profiling
 	if (const char* e = getenv("BRICKMAP_B200_NO_STOCK")) c->q_stock = c->q_stock && e[0] != '1';
-	CK(cudaFuncSetAttribute(frame_kernel_q<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)c->q_smem));
-	CK(cudaFuncSetAttribute(frame_kernel_q<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)c->q_smem));
-	CK(cudaFuncSetAttribute(frame_kernel_q<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)c->q_smem));
-	CK(cudaFuncSetAttribute(frame_kernel_q<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)c->q_smem));
-	CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, frame_kernel_q<false, true>, kQBlock, c->q_smem));
+	const size_t smem_max = (size_t)props_smem_optin(c->cfg.device);
+	const size_t q_queues = (size_t)(kQBlock / 32) * E_WORDS * kQueueEntries * 4, q_jobs = (size_t)kQBlock * kJobs * 16;
+	if (c->q_mode == Q_FAR && (size_t)sv.coarse_words * 8 + q_queues > smem_max) c->q_mode = Q_PLAIN;       // no room for the far words
+	if (c->q_mode == Q_DEFERRED && (size_t)sv.coarse_words * 4 + q_queues + q_jobs > smem_max) c->q_mode = Q_PLAIN;  // ... for the brick jobs
+	c->q_smem = (size_t)sv.coarse_words * (c->q_mode == Q_FAR ? 8 : 4) + q_queues + (c->q_mode == Q_DEFERRED ? q_jobs : 0);
+	if (c->q_smem > smem_max) c->use_quantum = false;
+	if (c->use_quantum) {
+		CK(cudaFuncSetAttribute(frame_kernel_q<true, Q_PLAIN>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)c->q_smem));
+		CK(cudaFuncSetAttribute(frame_kernel_q<false, Q_PLAIN>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)c->q_smem));
+		CK(cudaFuncSetAttribute(frame_kernel_q<true, Q_FAR>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)c->q_smem));
+		CK(cudaFuncSetAttribute(frame_kernel_q<false, Q_FAR>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)c->q_smem));
+		CK(cudaFuncSetAttribute(frame_kernel_q<true, Q_DEFERRED>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)c->q_smem));
+		CK(cudaFuncSetAttribute(frame_kernel_q<false, Q_DEFERRED>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)c->q_smem));
+		CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, frame_kernel_q<false, Q_DEFERRED>, kQBlock, c->q_smem));
+	}
 	if (per_sm < 1) c->use_quantum = false;
 	c->q_blocks = c->sm_count * (per_sm < 1 ? 1 : per_sm);
 	c->bound = true;
@@ -981,10 +1004,19 @@ static int launch_frame_kernels(bm_context* c, const FrameIO& io, bool count) {
 	}
 	if (count) frame_kernel<RECORD, true><<<blocks, kTile, c->frame_smem, c->stream>>>(c->fp, c->sv, io);
 	else if (RECORD || !c->use_quantum) frame_kernel<RECORD, false><<<blocks, kTile, c->frame_smem, c->stream>>>(c->fp, c->sv, io);
-	else if (c->q_stock && c->q_far) frame_kernel_q<true, true><<<c->q_blocks, kQBlock, c->q_smem, c->stream>>>(c->fp, c->sv, io, c->quantum);
-	else if (c->q_far) frame_kernel_q<false, true><<<c->q_blocks, kQBlock, c->q_smem, c->stream>>>(c->fp, c->sv, io, c->quantum);
-	else if (c->q_stock) frame_kernel_q<true, false><<<c->q_blocks, kQBlock, c->q_smem, c->stream>>>(c->fp, c->sv, io, c->quantum);
-	else frame_kernel_q<false, false><<<c->q_blocks, kQBlock, c->q_smem, c->stream>>>(c->fp, c->sv, io, c->quantum);
+	else {
+#define BM_LAUNCH_Q(STOCK, MODE) frame_kernel_q<STOCK, MODE><<<c->q_blocks, kQBlock, c->q_smem, c->stream>>>(c->fp, c->sv, io, c->quantum, c->min_share, c->descending)
+		if (c->q_stock) {
+			if (c->q_mode == Q_DEFERRED) BM_LAUNCH_Q(true, Q_DEFERRED);
+			else if (c->q_mode == Q_FAR) BM_LAUNCH_Q(true, Q_FAR);
+			else BM_LAUNCH_Q(true, Q_PLAIN);
+		} else {
+			if (c->q_mode == Q_DEFERRED) BM_LAUNCH_Q(false, Q_DEFERRED);
+			else if (c->q_mode == Q_FAR) BM_LAUNCH_Q(false, Q_FAR);
+			else BM_LAUNCH_Q(false, Q_PLAIN);
+		}
+#undef BM_LAUNCH_Q
+	}
 	CK(cudaGetLastError());
 	if (c->timing) CK(cudaEventRecord(e1, c->stream));
 	// the mask that was this frame's input becomes the next frame's output: the scan clears it

@@ -278,6 +278,34 @@ def test_throughput_kernel_matches_simple_kernel_on_the_stock_world(golden, stor
     assert [sf[k] for k in ("shadow_rays", "terminations", "unoccluded")] == [ss[k] for k in ("shadow_rays", "terminations", "unoccluded")]
 
 
+@pytest.mark.parametrize("variant", ["256lod", "4096"])
+def test_throughput_kernel_modes_agree(golden, stores, variant, monkeypatch):
+    """The throughput kernel's three traversal loops -- plain, far-block runs, deferred bricks -- and two scheduling settings
+    (fixed quantum; batches given up when they thin out) are different schedules of the same arithmetic: survivors bit for
+    bit, alpha exactly, radiance to 1e-5 (the order of the float atomics differs)."""
+    g = golden(variant)
+    store = stores(variant)
+    cfg = store.cfg
+    h, w = cfg.screen_height, cfg.screen_width
+    results = []
+    for mode, quantum, share in ((0, 64, 0), (1, 128, 0), (2, 64, 0), (2, 256, 16), (0, 256, 20)):
+        monkeypatch.setenv("BRICKMAP_B200_MODE", str(mode))
+        monkeypatch.setenv("BRICKMAP_B200_QUANTUM", str(quantum))
+        monkeypatch.setenv("BRICKMAP_B200_MIN_SHARE", str(share))
+        ren = renderer_for(g, store)  # the switches are read when the scene is bound
+        blit = torch.zeros(h, w, 4, dtype=torch.float32, device="cuda")
+        ren.render(blit, 3)
+        c = ren.counters()
+        st = ren.stats()
+        results.append((c.primary_ray_cnt, c.start_position, c.frame, st["shadow_rays"], st["terminations"], st["unoccluded"], ren.export_rays(), blit.cpu().numpy()))
+    ref = results[0]
+    for r in results[1:]:
+        assert r[:6] == ref[:6]
+        assert_records_equal(r[6], ref[6], what="survivors across traversal modes")
+        assert np.array_equal(r[7][..., 3], ref[7][..., 3])
+        assert_close_rel(r[7], ref[7], 1e-5, "accumulation across traversal modes")
+
+
 def test_ragged_sizes_match_oracle(oracle, golden):
     """Slot count not a multiple of the warp size or of a run, image not a multiple of anything, fewer slots than pixels and
     more slots than pixels (the cursor wraps inside a frame, kernel.cu:170-171)."""
