@@ -321,7 +321,7 @@ def main():
     except Exception:
         pass
     roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": (achieved / peak) if achieved else None, "traffic": traffic,
-                "kernel": "frame_kernel", "peak_source": peak_kind + " (MEASURED_PEAKS.json hbm_gbs, torch copy)",
+                "kernel": "frame_kernel_q", "peak_source": peak_kind + " (MEASURED_PEAKS.json hbm_gbs, torch copy)",
                 "algorithmic_bytes_per_ray": bytes_per_ray, "rays_per_launch": rays_per_launch, "kernel_ms_per_launch": kernel_ms / launches0,
                 "kernel_share_of_step": kernel_ms / ms if ms > 0 else None,
                 "per_ray": {"cell_steps": work["cell_steps"] / max(wrays, 1), "index_words_loaded": work["index_reads"] / max(wrays, 1),

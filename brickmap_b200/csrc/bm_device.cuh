@@ -120,16 +120,13 @@ struct SceneView {
 	                              // For a cell position p biased by one block (p' = p + (1 << coarse_shift)), b = p' >> coarse_shift:
 	                              // bit (b.x & 31) of word (b.z * coarse_nby + b.y) * coarse_roww + (b.x >> 5). The one cell a DDA can
 	                              // stand in outside the world falls into the border, so the empty-space loop needs no bounds test.
-	                              // Stored as PAIRS of words {near, far}: near = the bitmap above. far bit, where near is clear: the block and
-	                              // its 26 neighbours are all empty and inside the world, i.e. so is every cell within Chebyshev distance
-	                              // (block width) of any cell of the block. far bit, where near is set: the block is a BORDER block
 	int cells, cells_height;      // variables.h:17-18
 	int supergrid_xy;             // variables.h:12
 	float grid_size_f, grid_height_f;
 	int lod2, lod8;               // variables.h:25-27
 	uint32_t queue_size;          // variables.h:35
 	int coarse_shift, coarse_nby, coarse_roww;  // bitmap geometry (coarse_nby counts the border blocks, coarse_roww = words per row)
-	uint32_t coarse_words;        // words of ONE bitmap; the global array holds 2 * coarse_words
+	uint32_t coarse_words;
 	const uint32_t* fine;         // emptiness per cell: 64 bits per 4x4x4 block, bit (x&3) | (y&3)<<2 | (z&3)<<4 (global)
 	int fine_nx, fine_nxy;        // 4x4x4 blocks per row / per slab
 };
@@ -229,29 +226,6 @@ __device__ __forceinline__ void dda_step(Dda& a, int& step_axis) {
 	    "@my mov.s32 %6, 1;\n\t"
 	    "}"
 	    : "+r"(a.pos.x), "+r"(a.pos.y), "+r"(a.pos.z), "+f"(a.tmax.x), "+f"(a.tmax.y), "+f"(a.tmax.z), "=r"(step_axis)
-	    : "r"(a.stepi.x), "r"(a.stepi.y), "r"(a.stepi.z), "f"(a.tdelta.x), "f"(a.tdelta.y), "f"(a.tdelta.z));
-}
-
-// ... and without recording the axis (steps inside a run of cells known to be empty)
-__device__ __forceinline__ void dda_step_blind(Dda& a) {
-	asm("{\n\t"
-	    ".reg .pred pxy, pxz, pyz, mx, my, mz;\n\t"
-	    "setp.lt.f32 pxy, %3, %4;\n\t"
-	    "setp.lt.f32 pxz, %3, %5;\n\t"
-	    "setp.lt.f32 pyz, %4, %5;\n\t"
-	    "and.pred mx, pxy, pxz;\n\t"
-	    "not.pred pxy, pxy;\n\t"
-	    "and.pred my, pxy, pyz;\n\t"
-	    "or.pred mz, mx, my;\n\t"
-	    "not.pred mz, mz;\n\t"
-	    "@mx add.s32 %0, %0, %6;\n\t"
-	    "@my add.s32 %1, %1, %7;\n\t"
-	    "@mz add.s32 %2, %2, %8;\n\t"
-	    "@mx add.rn.f32 %3, %3, %9;\n\t"
-	    "@my add.rn.f32 %4, %4, %10;\n\t"
-	    "@mz add.rn.f32 %5, %5, %11;\n\t"
-	    "}"
-	    : "+r"(a.pos.x), "+r"(a.pos.y), "+r"(a.pos.z), "+f"(a.tmax.x), "+f"(a.tmax.y), "+f"(a.tmax.z)
 	    : "r"(a.stepi.x), "r"(a.stepi.y), "r"(a.stepi.z), "f"(a.tdelta.x), "f"(a.tdelta.y), "f"(a.tdelta.z));
 }
 
@@ -366,9 +340,9 @@ __device__ __forceinline__ bool trace_setup(const SceneView& sv, F3 origin, cons
 
 enum : int { TRACE_MISS = 0, TRACE_HIT = 1, TRACE_SUSPENDED = 2 };
 #ifndef BM_TRACE_CHUNK
-#define BM_TRACE_CHUNK 8
+#define BM_TRACE_CHUNK 16
 #endif
-constexpr int kTraceChunk = BM_TRACE_CHUNK;  // cell tests between two looks at the budget (and, deferred bricks: between two brick walks)
+constexpr int kTraceChunk = BM_TRACE_CHUNK;  // cell tests between two looks at the budget (8: 2509, 16: 2530 Mrays/s)
 
 // The DDA loop of intersect_voxel (voxel.cuh:192-259). `coarse_smem` is the block's shared-memory copy of the emptiness
 // bitmap. The DDA performs exactly the reference's sequence of floating-point steps; only the LOADS of index words for empty
@@ -377,14 +351,11 @@ constexpr int kTraceChunk = BM_TRACE_CHUNK;  // cell tests between two looks at 
 // return TRACE_SUSPENDED with the state to resume from (the cell the ray stands in has not been tested yet; it may be the
 // cell outside the world, which the resumed loop then detects).
 // Inside the loop (and in a suspended TraceState) the cell position is BIASED by one bitmap block, see SceneView::coarse.
-// FAR: `coarse_smem` holds {near, far} word pairs; where the far bit is set the block's 26 neighbours are empty and inside the
-// world, so as many cells as a block is wide (4 in the stock world) lie ahead empty whatever the direction: the loop takes
-// that many DDA steps without a test, then one more whose cell the next iteration tests (a test costs more than a step).
 // STOCK: the bitmap geometry of the reference's stock world (512 x 512 x 64 cells: blocks of 4^3 cells, 130 rows of 5 words
 // per slab) as compile-time constants.
-template <bool COUNT, bool BOUNDED, bool FAR = false, bool STOCK = false>
+template <bool COUNT, bool BOUNDED, bool STOCK = false>
 __device__ __forceinline__ int trace_run(const SceneView& sv, const uint32_t* coarse_smem, const F3 direction, F3& normal, float& distance, const I3 cam,
-                                         TraceState& ts, int budget, WorkCounters* wc, int min_lanes = 0) {
+                                         TraceState& ts, int budget, WorkCounters* wc, int min_lanes = 0, int inline_tests = 0x7FFFFFFF) {
 	const F3 origin = ts.origin;
 	const float tminn = ts.tminn;
 	Dda& a = ts.a;
@@ -406,24 +377,19 @@ __device__ __forceinline__ int trace_run(const SceneView& sv, const uint32_t* co
 		if (COUNT) wc->steps++;
 		const int bx = a.pos.x >> shift;
 		const int w = ((a.pos.z >> shift) * nby + (a.pos.y >> shift)) * roww + (bx >> 5);
-		uint32_t cw, fw = 0;
-		if (FAR) asm("ld.shared.v2.u32 {%0, %1}, [%2];" : "=r"(cw), "=r"(fw) : "r"(smem_base + (w << 3)));
-		else asm("ld.shared.u32 %0, [%1];" : "=r"(cw) : "r"(smem_base + (w << 2)));
-		uint32_t near_bit, far_bit;  // one mask, two AND-tests (the compiler's own form is shift + and + compare for each)
+		uint32_t cw;  // explicit shared-window load: keeps the address arithmetic short
+		asm("ld.shared.u32 %0, [%1];" : "=r"(cw) : "r"(smem_base + (w << 2)));
+		uint32_t near_bit;  // mask + AND-test (the compiler's own form is shift + and + compare)
 		asm("{\n\t"
 		    ".reg .b32 m;\n\t"
-		    "shf.l.wrap.b32 m, 0, 1, %2;\n\t"
-		    "and.b32 %0, %3, m;\n\t"
-		    "and.b32 %1, %4, m;\n\t"
+		    "shf.l.wrap.b32 m, 0, 1, %1;\n\t"
+		    "and.b32 %0, %2, m;\n\t"
 		    "}"
-		    : "=r"(near_bit), "=r"(far_bit)
-		    : "r"(bx), "r"(cw), "r"(fw));
-		const bool far = FAR && !COUNT && far_bit;
+		    : "=r"(near_bit)
+		    : "r"(bx), "r"(cw));
 		if (near_bit) {
 			const I3 p{ a.pos.x - bias, a.pos.y - bias, a.pos.z - bias };
-			// outside the world? With the far words at hand that is one more bit test: border blocks have BOTH bits set
-			if (FAR ? far_bit != 0u
-			        : ((unsigned)p.x >= (unsigned)sv.cells || (unsigned)p.y >= (unsigned)sv.cells || (unsigned)p.z >= (unsigned)sv.cells_height)) {  // voxel.cuh:256
+			if ((unsigned)p.x >= (unsigned)sv.cells || (unsigned)p.y >= (unsigned)sv.cells || (unsigned)p.z >= (unsigned)sv.cells_height) {  // voxel.cuh:256
 				if (COUNT) wc->steps--;  // not a cell test of the reference: its loop ended with the step that left the world
 				return TRACE_MISS;
 			}
@@ -458,6 +424,11 @@ __device__ __forceinline__ int trace_run(const SceneView& sv, const uint32_t* co
 								return TRACE_HIT;
 						}
 					} else if (index & BM_BRICK_LOADED_BIT) {  // voxel.cuh:222-227
+						// BOUNDED: a brick met later than the first `inline_tests` cell tests of this call is not walked now, with the
+						// few lanes that happen to be at a brick in this very iteration: the ray is suspended IN FRONT of the cell. Resumed,
+						// it tests the cell again first thing, next to the other rays of its batch that were suspended the same way, and
+						// they walk their bricks together. (normal was set above; the resumed test sets it again.)
+						if (BOUNDED && (budget - it) + (kTraceChunk - chunk) >= inline_tests) return TRACE_SUSPENDED;
 						const bm_brick* b = bricks_sc + (index & BM_BRICK_INDEX_BITS);
 						// both 32-byte halves of the brick on their way while the sub-DDA is set up (its loads are one word per step)
 						asm volatile("prefetch.global.L1 [%0];" ::"l"(b));
@@ -488,17 +459,6 @@ __device__ __forceinline__ int trace_run(const SceneView& sv, const uint32_t* co
 				}
 			}
 		}
-		if (far) {
-			// the block's neighbours are as wide as the block: that many steps stay inside the empty neighbourhood
-			if (STOCK) {
-				dda_step_blind(a);
-				dda_step_blind(a);
-				dda_step_blind(a);
-				dda_step_blind(a);
-			} else {
-				for (int k = bias < 8 ? bias : 8; k > 0; k--) dda_step_blind(a);
-			}
-		}
 		dda_step(a, step_axis);
 	}
 		if (BOUNDED) {
@@ -508,148 +468,6 @@ __device__ __forceinline__ int trace_run(const SceneView& sv, const uint32_t* co
 	}
 }
 
-
-// trace_run with DEFERRED BRICKS (throughput kernel). In trace_run a lane that reaches a loaded brick walks its 8^3 voxels on
-// the spot while the rest of the warp waits: a quarter of all issued instructions run with 6 of 32 lanes. Four out of five
-// bricks a ray enters are missed, so here the lane only notes the brick down (pointer, entry distance, entry axis: a "job" in
-// shared memory) and steps on as if it had missed. At the end of every chunk of kTraceChunk cell tests the lanes of the warp
-// walk their noted bricks TOGETHER, in the order they were met. A hit ends the ray there -- what the lane did after that
-// brick is dropped, which is exact: the steps past a missed brick are the steps the reference takes, and nothing with a
-// side effect (brick request, LoD hit, leaving the world) is acted on while a job is pending: the lane stops in front of it
-// and looks at that cell again once its bricks are resolved. `normal` is not touched by a noted brick that is missed; the
-// reference overwrites it there (voxel.cuh:203), but any later hit overwrites it again and a miss does not use it.
-constexpr int kJobs = 2;  // noted bricks per lane and chunk
-template <bool STOCK>
-__device__ __forceinline__ int trace_run_deferred(const SceneView& sv, const F3 direction, F3& normal, float& distance, const I3 cam, TraceState& ts, int budget,
-                                                  int min_lanes, uint32_t* jobs /* this lane's column of the warp's job area: word (j * 4 + f) * 32 */) {
-	const F3 origin = ts.origin;
-	const float tminn = ts.tminn;
-	Dda& a = ts.a;
-	int& step_axis = ts.step_axis;
-	const int shift = STOCK ? 2 : sv.coarse_shift;
-	const int nby = STOCK ? 130 : sv.coarse_nby, roww = STOCK ? 5 : sv.coarse_roww;
-	const int bias = 1 << shift;
-	uint32_t smem_base = (uint32_t)__cvta_generic_to_shared(bm_dyn_smem);
-	asm volatile("" : "+r"(smem_base));
-
-	int njobs = 0;
-	bool left_world = false;
-	for (int it = budget;;) {
-		for (int chunk = kTraceChunk; chunk > 0; chunk--) {
-			const int bx = a.pos.x >> shift;
-			const int w = ((a.pos.z >> shift) * nby + (a.pos.y >> shift)) * roww + (bx >> 5);
-			uint32_t cw;
-			asm("ld.shared.u32 %0, [%1];" : "=r"(cw) : "r"(smem_base + (w << 2)));
-			uint32_t near_bit;
-			asm("{\n\t"
-			    ".reg .b32 m;\n\t"
-			    "shf.l.wrap.b32 m, 0, 1, %1;\n\t"
-			    "and.b32 %0, %2, m;\n\t"
-			    "}"
-			    : "=r"(near_bit)
-			    : "r"(bx), "r"(cw));
-			if (near_bit) {
-				const I3 p{ a.pos.x - bias, a.pos.y - bias, a.pos.z - bias };
-				if ((unsigned)p.x >= (unsigned)sv.cells || (unsigned)p.y >= (unsigned)sv.cells || (unsigned)p.z >= (unsigned)sv.cells_height) {  // voxel.cuh:256
-					if (njobs == 0) return TRACE_MISS;
-					left_world = true;  // a miss unless one of the noted bricks is hit
-					break;
-				}
-				const int fb = (p.x >> 2) + (p.y >> 2) * sv.fine_nx + (p.z >> 2) * sv.fine_nxy;
-				const int fbit = (p.x & 3) | ((p.y & 3) << 2) | ((p.z & 3) << 4);
-				if ((__ldg(sv.fine + (size_t)fb * 2 + (fbit >> 5)) >> (fbit & 31)) & 1u) {
-					const int sc = (p.x >> 4) + (p.y >> 4) * sv.supergrid_xy + (p.z >> 4) * sv.supergrid_xy * sv.supergrid_xy;  // voxel.cuh:197
-					const int local = (p.x & 15) + (p.y & 15) * 16 + (p.z & 15) * 256;                                        // voxel.cuh:198
-					uint32_t* word = sv.flat_indices ? sv.flat_indices + (((size_t)sc << 12) + local) : sv.indices[sc] + local;
-					const bm_brick* const bricks_sc = sv.bricks[sc];
-					const uint32_t index = __ldg(word);
-					if (index) {
-						const int dx = cam.x - p.x, dy = cam.y - p.y, dz = cam.z - p.z;
-						const int lod_distance_squared = dx * dx + dy * dy + dz * dz;
-						const bool is_brick = !(lod_distance_squared > sv.lod8) && !(lod_distance_squared > sv.lod2) && (index & BM_BRICK_LOADED_BIT);  // voxel.cuh:212-222
-						if (is_brick && njobs < kJobs) {
-							const bm_brick* b = bricks_sc + (index & BM_BRICK_INDEX_BITS);
-							asm volatile("prefetch.global.L1 [%0];" ::"l"(b));
-							asm volatile("prefetch.global.L1 [%0];" ::"l"(reinterpret_cast<const char*>(b) + 32));
-							const float new_distance = step_axis != -1 ? comp(a.tmax, step_axis) - comp(a.tdelta, step_axis) : 0.f;
-							uint32_t* job = jobs + njobs * (4 * 32);
-							job[0] = (uint32_t)(uintptr_t)b;
-							job[32] = (uint32_t)((uintptr_t)b >> 32);
-							job[64] = __float_as_uint(new_distance);
-							job[96] = (uint32_t)(step_axis + 1);
-							njobs++;
-						} else if (njobs) {
-							break;  // stop in front of this cell; it is looked at again once the noted bricks are resolved
-						} else {
-							float new_distance = 0.f;
-							if (step_axis != -1) {
-								normal = axis_normal(a, step_axis);
-								new_distance = comp(a.tmax, step_axis) - comp(a.tdelta, step_axis);
-							}
-							float sub_distance = 0.f;
-							if (lod_distance_squared > sv.lod8) {  // voxel.cuh:212-214
-								distance = new_distance * 8.f + tminn;
-								return TRACE_HIT;
-							} else if (lod_distance_squared > sv.lod2) {  // voxel.cuh:215-220
-								const F3 x{ fmaf(direction.x, new_distance, origin.x), fmaf(direction.y, new_distance, origin.y), fmaf(direction.z, new_distance, origin.z) };
-								const F3 so{ fmaf(normal.x * 0.2f, -kEpsilon, x.x + x.x), fmaf(normal.y * 0.2f, -kEpsilon, x.y + x.y), fmaf(normal.z * 0.2f, -kEpsilon, x.z + x.z) };
-								if (intersect_byte(so, direction, a, normal, sub_distance, (index & BM_BRICK_LOD_BITS) >> 12)) {
-									distance = (new_distance * 8.f + sub_distance * 4.f) + tminn;
-									return TRACE_HIT;
-								}
-							} else if (index & BM_BRICK_LOADED_BIT) {  // only with kJobs == 0
-								const bm_brick* b = bricks_sc + (index & BM_BRICK_INDEX_BITS);
-								const F3 x{ fmaf(direction.x, new_distance, origin.x), fmaf(direction.y, new_distance, origin.y), fmaf(direction.z, new_distance, origin.z) };
-								const F3 so{ x.x * 8.f - normal.x * kEpsilon, x.y * 8.f - normal.y * kEpsilon, x.z * 8.f - normal.z * kEpsilon };
-								if (intersect_brick(so, direction, a, normal, sub_distance, b)) {
-									distance = (new_distance * 8.f + sub_distance) + tminn;
-									return TRACE_HIT;
-								}
-							} else if (index & BM_BRICK_UNLOADED_BIT) {  // voxel.cuh:228-244
-								const uint32_t old = atomicOr(word, BM_BRICK_REQUESTED_BIT);
-								if (!(old & BM_BRICK_REQUESTED_BIT)) {
-									const uint32_t load_index = atomicAdd(sv.load_queue_count, 1u);
-									if (load_index < sv.queue_size) {
-										sv.load_queue[3 * load_index + 0] = p.x;
-										sv.load_queue[3 * load_index + 1] = p.y;
-										sv.load_queue[3 * load_index + 2] = p.z;
-									} else {
-										atomicAnd(word, ~BM_BRICK_REQUESTED_BIT);
-									}
-								}
-								distance = new_distance * 8.f + tminn;
-								return TRACE_HIT;
-							}
-						}
-					}
-				}
-			}
-			dda_step(a, step_axis);
-		}
-		// ---- the warp's noted bricks, walked together (voxel.cuh:222-227), in the order each lane met them
-#pragma unroll 1
-		for (int j = 0; j < njobs; j++) {
-			const uint32_t* job = jobs + j * (4 * 32);
-			const bm_brick* b = reinterpret_cast<const bm_brick*>((uintptr_t)job[0] | ((uintptr_t)job[32] << 32));
-			const float new_distance = __uint_as_float(job[64]);
-			const int axis = (int)job[96] - 1;
-			F3 n = normal;
-			if (axis != -1) n = axis_normal(a, axis);
-			const F3 x{ fmaf(direction.x, new_distance, origin.x), fmaf(direction.y, new_distance, origin.y), fmaf(direction.z, new_distance, origin.z) };
-			const F3 so{ x.x * 8.f - n.x * kEpsilon, x.y * 8.f - n.y * kEpsilon, x.z * 8.f - n.z * kEpsilon };
-			float sub_distance = 0.f;
-			if (intersect_brick(so, direction, a, n, sub_distance, b)) {
-				normal = n;
-				distance = (new_distance * 8.f + sub_distance) + tminn;
-				return TRACE_HIT;
-			}
-		}
-		njobs = 0;
-		if (left_world) return TRACE_MISS;
-		it -= kTraceChunk;
-		if (it <= 0 || __popc(__activemask()) < min_lanes) return TRACE_SUSPENDED;
-	}
-}
 
 // intersect_voxel, voxel.cuh:135-261
 template <bool COUNT>

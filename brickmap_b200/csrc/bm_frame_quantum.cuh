@@ -22,7 +22,7 @@ namespace bm {
 #ifndef BM_QBLOCK
 #define BM_QBLOCK 1024
 #endif
-constexpr int kQBlock = BM_QBLOCK;  // 32 warps, one block per SM (shared memory: bitmap 46 KiB [92 KiB with the far words] + 32 queues 128 KiB).
+constexpr int kQBlock = BM_QBLOCK;  // 32 warps, one block per SM (shared memory: bitmap 46 KiB + 32 queues 128 KiB).
                                     // Measured on the benchmark view: 512 threads 2.06, 768 2.35, 1024 2.49 Grays/s
 constexpr int kQueueEntries = 64;
 enum : int {
@@ -40,16 +40,12 @@ enum : int { K_NONE = -1, K_EXTEND = 0, K_SHADOW = 1, K_SHADOW_NEW = 2 };
 #define QF(field, e) q[(field) * kQueueEntries + (e)]
 #define QU(field, e) reinterpret_cast<uint32_t*>(q)[(field) * kQueueEntries + (e)]
 
-// MODE: 0 = trace_run, 1 = trace_run with the far words (five-step runs), 2 = trace_run_deferred (bricks noted and walked together)
-enum : int { Q_PLAIN = 0, Q_FAR = 1, Q_DEFERRED = 2 };
-template <bool STOCK, int MODE>
-__global__ void __launch_bounds__(kQBlock, 1) frame_kernel_q(const FrameParams fp, const SceneView sv, const FrameIO io, const int quantum, const int min_share, const int descending) {
+template <bool STOCK>
+__global__ void __launch_bounds__(kQBlock, 1) frame_kernel_q(const FrameParams fp, const SceneView sv, const FrameIO io, const int quantum, const int min_share, const int descending, const int inline_tests) {
 	extern __shared__ uint32_t s_coarse[];
 	DeviceState* st = io.st;
 	if (st->done) return;
-	constexpr bool FAR = MODE == Q_FAR;
-	if (FAR) for (uint32_t i = threadIdx.x; i < 2 * sv.coarse_words; i += blockDim.x) s_coarse[i] = __ldg(sv.coarse + i);  // {near, far} pairs
-	else for (uint32_t i = threadIdx.x; i < sv.coarse_words; i += blockDim.x) s_coarse[i] = __ldg(sv.coarse + 2 * i);    // near words only
+	for (uint32_t i = threadIdx.x; i < sv.coarse_words; i += blockDim.x) s_coarse[i] = __ldg(sv.coarse + i);
 	const uint32_t* coarse = s_coarse;
 	__syncthreads();
 
@@ -58,10 +54,7 @@ __global__ void __launch_bounds__(kQBlock, 1) frame_kernel_q(const FrameParams f
 	const uint32_t frame = st->frame;
 	const uint32_t lane = threadIdx.x & 31;
 	const uint32_t lt_mask = (1u << lane) - 1u;
-	float* q = reinterpret_cast<float*>(s_coarse + (FAR ? 2 : 1) * sv.coarse_words) + (threadIdx.x >> 5) * (E_WORDS * kQueueEntries);
-	// Q_DEFERRED: the warp's brick jobs behind all queues, kJobs x 4 words per lane, lane-interleaved
-	uint32_t* jobs = reinterpret_cast<uint32_t*>(s_coarse + (FAR ? 2 : 1) * sv.coarse_words) + (kQBlock / 32) * (E_WORDS * kQueueEntries) +
-	                 (threadIdx.x >> 5) * (kJobs * 4 * 32) + lane;
+	float* q = reinterpret_cast<float*>(s_coarse + sv.coarse_words) + (threadIdx.x >> 5) * (E_WORDS * kQueueEntries);
 	uint32_t qn = 0;  // entries in the warp's queue (warp-uniform)
 	uint32_t n_shadow = 0, n_term = 0, n_unocc = 0;
 
@@ -156,11 +149,10 @@ __global__ void __launch_bounds__(kQBlock, 1) frame_kernel_q(const FrameParams f
 		// still at it; rays that entered the world from outside cannot be suspended (see above) and run to their end
 		const int min_lanes = (__popc(__ballot_sync(0xFFFFFFFFu, tracing)) * min_share) >> 5;
 		if (tracing) {
-			const bool pinned = ts.tminn > 0.f;
-			if (MODE == Q_DEFERRED)
-				status = trace_run_deferred<STOCK>(sv, direction, normal, distance, fp.cam_cell, ts, pinned ? 0x3FFFFFF8 : quantum, pinned ? 0 : min_lanes, jobs);
-			else
-				status = trace_run<false, true, FAR, STOCK>(sv, coarse, direction, normal, distance, fp.cam_cell, ts, pinned ? 0x3FFFFFF8 : quantum, &wc, pinned ? 0 : min_lanes);
+			// no suspending where it cannot regroup anything: rays that entered from outside (see above), and the last batch of a
+			// warp whose queue and slot pool are both empty
+			const bool pinned = ts.tminn > 0.f || (pool_dry && qn == 0);
+			status = trace_run<false, true, STOCK>(sv, coarse, direction, normal, distance, fp.cam_cell, ts, pinned ? 0x3FFFFFF8 : quantum, &wc, pinned ? 0 : min_lanes, pinned ? 0x7FFFFFFF : inline_tests);
 		}
 		__syncwarp();  // lanes whose ray ended early wait here: they are shaded together, not interleaved with the tracing lanes
 

@@ -1,25 +1,26 @@
 // Kernels and C ABI of the B200 path tracer (include/brickmap_b200.h).
 //
 // Execution model (B200-first, not the reference's five atomically-fed wavefront kernels, kernel.cu:412-420):
-//   * ONE kernel per frame (frame_kernel). A thread owns one of the frame's N segment slots from ray generation (or
-//     survivor fetch) through extend, shade and its shadow ray, with the path vertex in registers; the 64-byte RayQueue
-//     record is touched once on the way in (survivors only) and once on the way out (survivors only), as four 128-bit
-//     transactions; shadow rays never leave registers. The reference moves ~310 B per slot through L2/HBM.
+//   * ONE kernel per frame. A slot of the frame goes from ray generation (or survivor fetch) through extend, shade and its
+//     shadow ray without leaving the SM; the 64-byte RayQueue record is touched once on the way in (survivors only) and once
+//     on the way out (survivors only), as four 128-bit transactions. The reference moves ~310 B per slot through L2/HBM.
+//   * Two frame kernels with identical results. frame_kernel_q (bm_frame_quantum.cuh) is the throughput path of bm_render:
+//     a warp traces 32 rays at a time and suspends / regroups them through a work queue in shared memory, so that long rays
+//     do not hold 31 idle lanes. frame_kernel (below) keeps one thread on one slot from start to end; it serves
+//     bm_launch_frame (RECORD: every buffer the reference's kernels leave), the work counters (COUNT) and very large worlds.
 //   * Warps pull runs of 128 consecutive slots with one atomic per run (the reference: one same-address atomic per ray per
-//     kernel, kernel.cu:158,228,245,330). Survivors are written sparse at their slot and flagged in a bitmask with one
-//     __ballot_sync per warp; a 1-block scan kernel turns the mask popcounts into the next frame's slot numbering (search +
-//     select in survivor_ptr), advances the pixel cursor and the frame counter on the device (set_wavefront_globals,
-//     kernel.cu:122-139). No block barrier inside a frame, no host round trip between frames.
-//   * Two derived emptiness bitmaps: 1 bit per 4x4x4 cells in shared memory (32 KiB at reference dims, one LDS per DDA
-//     step) and 1 bit per cell in global memory (2 MiB, touched only inside non-empty blocks). The DDA performs the
-//     reference's exact float step sequence (hand-scheduled in PTX, 21 SASS instructions per step) but loads an index word
-//     only for cells that are really non-empty (2.2 per ray instead of the reference's 88). Index words of a flat arena are
-//     addressed directly (no pointer-table dependent load, voxel.cuh:197-198).
-//   * 64 registers per thread -> 4 blocks of 256 threads per SM.
+//     kernel, kernel.cu:158,228,245,330). Survivors are written sparse at their slot and flagged in a bitmask; a 1-block scan
+//     kernel turns the mask popcounts into the next frame's slot numbering (search + select in survivor_ptr), advances the
+//     pixel cursor and the frame counter on the device (set_wavefront_globals, kernel.cu:122-139). No block barrier inside a
+//     frame, no host round trip between frames.
+//   * Two derived emptiness bitmaps: 1 bit per 4x4x4 cells with a one-block border in shared memory (46 KiB at reference dims,
+//     one LDS per DDA step, no bounds test in empty space) and 1 bit per cell in global memory (2 MiB, touched only inside
+//     non-empty blocks). The DDA performs the reference's exact float step sequence (hand-scheduled in PTX) but loads an
+//     index word only for cells that are really non-empty (2.2 per ray instead of the reference's 88). Index words of a flat
+//     arena are addressed directly (no pointer-table dependent load, voxel.cuh:197-198).
 //   * Slot order == "the reference scheduled one thread at a time", so seeds (kernel.cu:165,252) and results are
 //     reproducible and comparable with the reference launched <<<1,1>>>.
-// A warp-level state-machine variant (lane refill, deferred shading, exact multi-step jumps through empty blocks) was built
-// and measured; it produced identical results but did not beat this kernel (profiles/README.md, profiles/experiments/).
+// Variants that were built, verified and measured slower are listed in DESIGN.md section 4 (sources: profiles/experiments/).
 #include <cuda_runtime.h>
 
 #include <cmath>
@@ -130,7 +131,7 @@ __global__ void __launch_bounds__(kTile, 4) frame_kernel(const FrameParams fp, c
 	extern __shared__ uint32_t s_coarse[];
 	DeviceState* st = io.st;
 	if (st->done) return;
-	for (uint32_t i = threadIdx.x; i < sv.coarse_words; i += blockDim.x) s_coarse[i] = __ldg(sv.coarse + 2 * i);  // near words only
+	for (uint32_t i = threadIdx.x; i < sv.coarse_words; i += blockDim.x) s_coarse[i] = __ldg(sv.coarse + i);
 	const uint32_t* coarse = s_coarse;
 	__syncthreads();
 
@@ -437,31 +438,7 @@ __global__ void coarse_build_kernel(const SceneView sv, uint32_t* coarse) {
 				if (sv.indices[sc][local]) { any = true; break; }
 			}
 	const uint32_t ballot = __ballot_sync(0xFFFFFFFFu, any);
-	if (lane == 0) coarse[2 * word] = ballot;
-}
-
-// far words of the {near, far} pairs (SceneView::coarse): block and its 26 neighbours all empty, or -- together with the near
-// bit -- border block. One thread per block bit.
-__global__ void far_build_kernel(const SceneView sv, uint32_t* coarse) {
-	const uint32_t gid = blockIdx.x * blockDim.x + threadIdx.x;
-	const uint32_t word = gid >> 5, lane = gid & 31;
-	if (word >= sv.coarse_words) return;
-	const int side = 1 << sv.coarse_shift;
-	const int nbx = sv.coarse_roww * 32, nby = sv.coarse_nby, nbz = (int)(sv.coarse_words / (uint32_t)(sv.coarse_roww * sv.coarse_nby));
-	const int row = word / sv.coarse_roww, bx = (int)((word % sv.coarse_roww) << 5) + (int)lane;
-	const int by = row % nby, bz = row / nby;
-	const bool border = bx < 1 || by < 1 || bz < 1 || (bx - 1) * side >= sv.cells || (by - 1) * side >= sv.cells || (bz - 1) * side >= sv.cells_height;
-	bool far = true;
-	for (int dz = -1; dz <= 1 && far; dz++)
-		for (int dy = -1; dy <= 1 && far; dy++)
-			for (int dx = -1; dx <= 1; dx++) {
-				const int x = bx + dx, y = by + dy, z = bz + dz;
-				if (x < 0 || y < 0 || z < 0 || x >= nbx || y >= nby || z >= nbz) { far = false; break; }
-				const uint32_t w = coarse[2 * ((size_t)(z * nby + y) * sv.coarse_roww + (x >> 5))];
-				if ((w >> (x & 31)) & 1u) { far = false; break; }
-			}
-	const uint32_t ballot = __ballot_sync(0xFFFFFFFFu, far || border);
-	if (lane == 0) coarse[2 * word + 1] = ballot;
+	if (lane == 0) coarse[word] = ballot;
 }
 
 // per-cell emptiness, 64 bits per 4x4x4 block of cells
@@ -494,7 +471,7 @@ __global__ void flat_check_kernel(uint32_t* const* indices, uint32_t n, uint32_t
 
 __global__ void trace_kernel(const SceneView sv, I3 cam, size_t n, const float* origins, const float* directions, float* normals, float* distances, uint8_t* hits) {
 	extern __shared__ uint32_t s_coarse[];
-	for (uint32_t i = threadIdx.x; i < sv.coarse_words; i += blockDim.x) s_coarse[i] = __ldg(sv.coarse + 2 * i);  // near words only
+	for (uint32_t i = threadIdx.x; i < sv.coarse_words; i += blockDim.x) s_coarse[i] = __ldg(sv.coarse + i);
 	const uint32_t* coarse = s_coarse;
 	__syncthreads();
 	for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
@@ -585,12 +562,12 @@ struct bm_context {
 	size_t frame_smem = 0;
 	// throughput kernel (frame_kernel_q)
 	bool use_quantum = true;  // BRICKMAP_B200_SIMPLE_KERNEL=1 switches the throughput path back to frame_kernel
-	int quantum = 128;        // BRICKMAP_B200_QUANTUM (cell tests per lane and batch; 128 measured best on the benchmark view)
-	int min_share = 0;        // BRICKMAP_B200_MIN_SHARE: a batch is given up when fewer than min_share / 32 of its tracing lanes are left
+	int quantum = 256;        // BRICKMAP_B200_QUANTUM: cell tests per lane and batch at most (with min_share 16: 64 -> 2440, 128 -> 2478, 256 -> 2494 Mrays/s)
+	int min_share = 16;       // BRICKMAP_B200_MIN_SHARE: a batch is given up when fewer than min_share / 32 of its tracing lanes are left
+	int inline_tests = 0x7FFFFFFF;  // BRICKMAP_B200_INLINE_TESTS: bricks met after this many cell tests of a batch suspend the ray (trace_run)
 	int descending = 0;       // BRICKMAP_B200_DESCENDING: hand out slot runs from the end of the frame
 	int q_blocks = 0;
 	bool q_stock = false;
-	int q_mode = 0;           // BRICKMAP_B200_MODE: Q_PLAIN / Q_FAR / Q_DEFERRED (bm_frame_quantum.cuh)
 	size_t q_smem = 0;
 };
 
@@ -786,14 +763,12 @@ int bm_scene_bind(bm_context* c, bm_gpu_scene scene) {
 	sv.coarse_words = (uint32_t)words;
 	cudaFree(c->d_coarse);
 	c->d_coarse = nullptr;
-	CK(cudaMalloc(&c->d_coarse, (size_t)sv.coarse_words * 8));  // {near, far} pairs
+	CK(cudaMalloc(&c->d_coarse, (size_t)sv.coarse_words * 4));
 	sv.coarse = nullptr;
 	sv.flat_indices = nullptr;
 	coarse_build_kernel<<<(sv.coarse_words * 32 + 255) / 256, 256, 0, c->stream>>>(sv, c->d_coarse);
 	CK(cudaGetLastError());
-	far_build_kernel<<<(sv.coarse_words * 32 + 255) / 256, 256, 0, c->stream>>>(sv, c->d_coarse);
-	CK(cudaGetLastError());
-	c->launches += 1;
+
 	sv.fine = nullptr;
 	sv.fine_nx = (sv.cells + 3) >> 2;
 	sv.fine_nxy = sv.fine_nx * sv.fine_nx;
@@ -831,26 +806,18 @@ int bm_scene_bind(bm_context* c, bm_gpu_scene scene) {
 	if (const char* e = getenv("BRICKMAP_B200_SIMPLE_KERNEL")) c->use_quantum = e[0] != '1';
 	if (const char* e = getenv("BRICKMAP_B200_QUANTUM")) c->quantum = atoi(e) > 0 ? atoi(e) : c->quantum;
 	c->quantum = (c->quantum + kTraceChunk - 1) / kTraceChunk * kTraceChunk;
+	if (const char* e = getenv("BRICKMAP_B200_INLINE_TESTS")) c->inline_tests = atoi(e) > 0 ? atoi(e) : c->inline_tests;
 	if (const char* e = getenv("BRICKMAP_B200_DESCENDING")) c->descending = e[0] == '1';
 	if (const char* e = getenv("BRICKMAP_B200_MIN_SHARE")) c->min_share = atoi(e) >= 0 && atoi(e) <= 32 ? atoi(e) : c->min_share;
 	if (sv.cells + (2 << shift) > 65535 || sv.cells_height + (2 << shift) > 4095) c->use_quantum = false;  // queue entries pack the biased cell position into 16 + 16 + 12 bits
 	c->q_stock = sv.coarse_shift == 2 && sv.coarse_nby == 130 && sv.coarse_roww == 5;  // the stock world's bitmap geometry is compiled in
-	if (const char* e = getenv("BRICKMAP_B200_MODE")) c->q_mode = atoi(e) >= 0 && atoi(e) <= 2 ? atoi(e) : c->q_mode;  // A/B switches for profiling
-	if (const char* e = getenv("BRICKMAP_B200_NO_STOCK")) c->q_stock = c->q_stock && e[0] != '1';
-	const size_t smem_max = (size_t)props_smem_optin(c->cfg.device);
-	const size_t q_queues = (size_t)(kQBlock / 32) * E_WORDS * kQueueEntries * 4, q_jobs = (size_t)kQBlock * kJobs * 16;
-	if (c->q_mode == Q_FAR && (size_t)sv.coarse_words * 8 + q_queues > smem_max) c->q_mode = Q_PLAIN;       // no room for the far words
-	if (c->q_mode == Q_DEFERRED && (size_t)sv.coarse_words * 4 + q_queues + q_jobs > smem_max) c->q_mode = Q_PLAIN;  // ... for the brick jobs
-	c->q_smem = (size_t)sv.coarse_words * (c->q_mode == Q_FAR ? 8 : 4) + q_queues + (c->q_mode == Q_DEFERRED ? q_jobs : 0);
-	if (c->q_smem > smem_max) c->use_quantum = false;
+	if (const char* e = getenv("BRICKMAP_B200_NO_STOCK")) c->q_stock = c->q_stock && e[0] != '1';  // A/B switch for profiling
+	c->q_smem = (size_t)sv.coarse_words * 4 + (size_t)(kQBlock / 32) * E_WORDS * kQueueEntries * 4;
+	if (c->q_smem > (size_t)props_smem_optin(c->cfg.device)) c->use_quantum = false;
 	if (c->use_quantum) {
-		CK(cudaFuncSetAttribute(frame_kernel_q<true, Q_PLAIN>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)c->q_smem));
-		CK(cudaFuncSetAttribute(frame_kernel_q<false, Q_PLAIN>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)c->q_smem));
-		CK(cudaFuncSetAttribute(frame_kernel_q<true, Q_FAR>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)c->q_smem));
-		CK(cudaFuncSetAttribute(frame_kernel_q<false, Q_FAR>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)c->q_smem));
-		CK(cudaFuncSetAttribute(frame_kernel_q<true, Q_DEFERRED>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)c->q_smem));
-		CK(cudaFuncSetAttribute(frame_kernel_q<false, Q_DEFERRED>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)c->q_smem));
-		CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, frame_kernel_q<false, Q_DEFERRED>, kQBlock, c->q_smem));
+		CK(cudaFuncSetAttribute(frame_kernel_q<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)c->q_smem));
+		CK(cudaFuncSetAttribute(frame_kernel_q<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)c->q_smem));
+		CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, frame_kernel_q<false>, kQBlock, c->q_smem));
 	}
 	if (per_sm < 1) c->use_quantum = false;
 	c->q_blocks = c->sm_count * (per_sm < 1 ? 1 : per_sm);
@@ -1004,19 +971,8 @@ static int launch_frame_kernels(bm_context* c, const FrameIO& io, bool count) {
 	}
 	if (count) frame_kernel<RECORD, true><<<blocks, kTile, c->frame_smem, c->stream>>>(c->fp, c->sv, io);
 	else if (RECORD || !c->use_quantum) frame_kernel<RECORD, false><<<blocks, kTile, c->frame_smem, c->stream>>>(c->fp, c->sv, io);
-	else {
-#define BM_LAUNCH_Q(STOCK, MODE) frame_kernel_q<STOCK, MODE><<<c->q_blocks, kQBlock, c->q_smem, c->stream>>>(c->fp, c->sv, io, c->quantum, c->min_share, c->descending)
-		if (c->q_stock) {
-			if (c->q_mode == Q_DEFERRED) BM_LAUNCH_Q(true, Q_DEFERRED);
-			else if (c->q_mode == Q_FAR) BM_LAUNCH_Q(true, Q_FAR);
-			else BM_LAUNCH_Q(true, Q_PLAIN);
-		} else {
-			if (c->q_mode == Q_DEFERRED) BM_LAUNCH_Q(false, Q_DEFERRED);
-			else if (c->q_mode == Q_FAR) BM_LAUNCH_Q(false, Q_FAR);
-			else BM_LAUNCH_Q(false, Q_PLAIN);
-		}
-#undef BM_LAUNCH_Q
-	}
+	else if (c->q_stock) frame_kernel_q<true><<<c->q_blocks, kQBlock, c->q_smem, c->stream>>>(c->fp, c->sv, io, c->quantum, c->min_share, c->descending, c->inline_tests);
+	else frame_kernel_q<false><<<c->q_blocks, kQBlock, c->q_smem, c->stream>>>(c->fp, c->sv, io, c->quantum, c->min_share, c->descending, c->inline_tests);
 	CK(cudaGetLastError());
 	if (c->timing) CK(cudaEventRecord(e1, c->stream));
 	// the mask that was this frame's input becomes the next frame's output: the scan clears it

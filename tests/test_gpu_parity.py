@@ -279,19 +279,23 @@ def test_throughput_kernel_matches_simple_kernel_on_the_stock_world(golden, stor
 
 
 @pytest.mark.parametrize("variant", ["256lod", "4096"])
-def test_throughput_kernel_modes_agree(golden, stores, variant, monkeypatch):
-    """The throughput kernel's three traversal loops -- plain, far-block runs, deferred bricks -- and two scheduling settings
-    (fixed quantum; batches given up when they thin out) are different schedules of the same arithmetic: survivors bit for
-    bit, alpha exactly, radiance to 1e-5 (the order of the float atomics differs)."""
+def test_throughput_kernel_schedules_agree(golden, stores, variant, monkeypatch):
+    """How long a batch runs before its unfinished rays are suspended (fixed quantum; given up early when the warp thins out;
+    suspended in front of bricks), in which order slot runs are handed out and whether the stock world's bitmap geometry is
+    compiled in are schedules / code paths of the same arithmetic:
+    survivors bit for bit, alpha exactly, radiance to 1e-5 (the order of the float atomics differs)."""
     g = golden(variant)
     store = stores(variant)
     cfg = store.cfg
     h, w = cfg.screen_height, cfg.screen_width
     results = []
-    for mode, quantum, share in ((0, 64, 0), (1, 128, 0), (2, 64, 0), (2, 256, 16), (0, 256, 20)):
-        monkeypatch.setenv("BRICKMAP_B200_MODE", str(mode))
+    for quantum, share, no_stock, inline, descending in ((64, 0, 0, 0, 0), (16, 0, 0, 0, 0), (256, 16, 0, 0, 0), (512, 28, 0, 0, 1), (256, 16, 1, 0, 0),
+                                                         (256, 16, 0, 1, 0), (128, 8, 0, 3, 1)):
         monkeypatch.setenv("BRICKMAP_B200_QUANTUM", str(quantum))
         monkeypatch.setenv("BRICKMAP_B200_MIN_SHARE", str(share))
+        monkeypatch.setenv("BRICKMAP_B200_NO_STOCK", str(no_stock))
+        monkeypatch.setenv("BRICKMAP_B200_INLINE_TESTS", str(inline))  # 0 = default: bricks are always walked where they are met
+        monkeypatch.setenv("BRICKMAP_B200_DESCENDING", str(descending))
         ren = renderer_for(g, store)  # the switches are read when the scene is bound
         blit = torch.zeros(h, w, 4, dtype=torch.float32, device="cuda")
         ren.render(blit, 3)
@@ -301,9 +305,9 @@ def test_throughput_kernel_modes_agree(golden, stores, variant, monkeypatch):
     ref = results[0]
     for r in results[1:]:
         assert r[:6] == ref[:6]
-        assert_records_equal(r[6], ref[6], what="survivors across traversal modes")
+        assert_records_equal(r[6], ref[6], what="survivors across schedules")
         assert np.array_equal(r[7][..., 3], ref[7][..., 3])
-        assert_close_rel(r[7], ref[7], 1e-5, "accumulation across traversal modes")
+        assert_close_rel(r[7], ref[7], 1e-5, "accumulation across schedules")
 
 
 def test_ragged_sizes_match_oracle(oracle, golden):
