@@ -127,8 +127,10 @@ struct SceneView {
 	uint32_t queue_size;          // variables.h:35
 	int coarse_shift, coarse_nby, coarse_roww;  // bitmap geometry (coarse_nby counts the border blocks, coarse_roww = words per row)
 	uint32_t coarse_words;
-	const uint32_t* fine;         // emptiness per cell: 64 bits per 4x4x4 block, bit (x&3) | (y&3)<<2 | (z&3)<<4 (global)
-	int fine_nx, fine_nxy;        // 4x4x4 blocks per row / per slab
+	const uint32_t* fine;         // emptiness per cell (global): 64 bits per 4x4x4 cells of the BIASED position space (p' = p + (1 << coarse_shift)),
+	                              // bit (x'&3) | (y'&3)<<2 | (z'&3)<<4 of pair (z'>>2) * fine_nxy + (y'>>2) * fine_nx + (x'>>2); cells outside the
+	                              // world have their bit set. With coarse_shift == 2 the grid is the coarse bitmap's: fine_nx = 32 * coarse_roww
+	int fine_nx, fine_nxy;        // pairs per row / per slab
 };
 
 struct WorkCounters {
@@ -388,20 +390,23 @@ __device__ __forceinline__ int trace_run(const SceneView& sv, const uint32_t* co
 		    : "=r"(near_bit)
 		    : "r"(bx), "r"(cw));
 		if (near_bit) {
-			const I3 p{ a.pos.x - bias, a.pos.y - bias, a.pos.z - bias };
-			if ((unsigned)p.x >= (unsigned)sv.cells || (unsigned)p.y >= (unsigned)sv.cells || (unsigned)p.z >= (unsigned)sv.cells_height) {  // voxel.cuh:256
-				if (COUNT) wc->steps--;  // not a cell test of the reference: its loop ended with the step that left the world
-				return TRACE_MISS;
-			}
-			const int fb = (p.x >> 2) + (p.y >> 2) * sv.fine_nx + (p.z >> 2) * sv.fine_nxy;
-			const int fbit = (p.x & 3) | ((p.y & 3) << 2) | ((p.z & 3) << 4);
-			if ((__ldg(sv.fine + (size_t)fb * 2 + (fbit >> 5)) >> (fbit & 31)) & 1u) {
+			// one bit per cell next: 64 bits per 4^3 cells of the BIASED position space, ones outside the world, so that the exit test
+			// is made only for cells that are non-empty or outside (with blocks of 4^3 cells the pair's index is the block bit's)
+			const int fbit = (a.pos.x & 3) | ((a.pos.y & 3) << 2) | ((a.pos.z & 3) << 4);
+			const uint32_t fidx = shift == 2 ? (uint32_t)((w << 5) + (bx & 31)) : (uint32_t)((a.pos.x >> 2) + (a.pos.y >> 2) * sv.fine_nx + (a.pos.z >> 2) * sv.fine_nxy);
+			if ((__ldg(sv.fine + (size_t)fidx * 2 + (fbit >> 5)) >> (fbit & 31)) & 1u) {
+				const I3 p{ a.pos.x - bias, a.pos.y - bias, a.pos.z - bias };
+				if ((unsigned)p.x >= (unsigned)sv.cells || (unsigned)p.y >= (unsigned)sv.cells || (unsigned)p.z >= (unsigned)sv.cells_height) {  // voxel.cuh:256
+					if (COUNT) wc->steps--;  // not a cell test of the reference: its loop ended with the step that left the world
+					return TRACE_MISS;
+				}
 				const int sc = (p.x >> 4) + (p.y >> 4) * sv.supergrid_xy + (p.z >> 4) * sv.supergrid_xy * sv.supergrid_xy;  // voxel.cuh:197
 				const int local = (p.x & 15) + (p.y & 15) * 16 + (p.z & 15) * 256;                                        // voxel.cuh:198
 				uint32_t* word = sv.flat_indices ? sv.flat_indices + (((size_t)sc << 12) + local) : sv.indices[sc] + local;
 				// the per-cell bit is set iff the index word is non-zero: what the word will be needed for can start now, the
 				// brick-table entry is loaded alongside the word instead of after it
-				const bm_brick* const bricks_sc = sv.bricks[sc];
+				const bm_brick* bricks_sc;  // (volatile: the compiler would sink the load below the test of the word again)
+				asm volatile("ld.global.nc.u64 %0, [%1];" : "=l"(bricks_sc) : "l"(sv.bricks + sc));
 				const uint32_t index = __ldg(word);
 				if (COUNT) wc->index_reads++;
 				if (index) {

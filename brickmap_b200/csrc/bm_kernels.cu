@@ -441,20 +441,24 @@ __global__ void coarse_build_kernel(const SceneView sv, uint32_t* coarse) {
 	if (lane == 0) coarse[word] = ballot;
 }
 
-// per-cell emptiness, 64 bits per 4x4x4 block of cells
+// per-cell emptiness, 64 bits per 4x4x4 cells of the biased position space, ones outside the world (SceneView::fine)
 __global__ void fine_build_kernel(const SceneView sv, uint32_t* fine, uint32_t nblocks) {
 	const uint32_t b = blockIdx.x * blockDim.x + threadIdx.x;
 	if (b >= nblocks) return;
+	const int bias = 1 << sv.coarse_shift;
 	const int bx = b % sv.fine_nx, by = (b / sv.fine_nx) % (sv.fine_nxy / sv.fine_nx), bz = b / sv.fine_nxy;
 	uint32_t lo = 0, hi = 0;
 	for (int z = 0; z < 4; z++)
 		for (int y = 0; y < 4; y++)
 			for (int x = 0; x < 4; x++) {
-				const int px = bx * 4 + x, py = by * 4 + y, pz = bz * 4 + z;
-				if (px >= sv.cells || py >= sv.cells || pz >= sv.cells_height) continue;
-				const int sc = (px >> 4) + (py >> 4) * sv.supergrid_xy + (pz >> 4) * sv.supergrid_xy * sv.supergrid_xy;
-				const int local = (px & 15) + (py & 15) * 16 + (pz & 15) * 256;
-				if (sv.indices[sc][local]) {
+				const int px = bx * 4 + x - bias, py = by * 4 + y - bias, pz = bz * 4 + z - bias;
+				bool set = true;
+				if (px >= 0 && py >= 0 && pz >= 0 && px < sv.cells && py < sv.cells && pz < sv.cells_height) {
+					const int sc = (px >> 4) + (py >> 4) * sv.supergrid_xy + (pz >> 4) * sv.supergrid_xy * sv.supergrid_xy;
+					const int local = (px & 15) + (py & 15) * 16 + (pz & 15) * 256;
+					set = sv.indices[sc][local] != 0;
+				}
+				if (set) {
 					const int bit = x | (y << 2) | (z << 4);
 					if (bit < 32) lo |= 1u << bit; else hi |= 1u << (bit - 32);
 				}
@@ -770,9 +774,17 @@ int bm_scene_bind(bm_context* c, bm_gpu_scene scene) {
 	CK(cudaGetLastError());
 
 	sv.fine = nullptr;
-	sv.fine_nx = (sv.cells + 3) >> 2;
-	sv.fine_nxy = sv.fine_nx * sv.fine_nx;
-	const uint32_t nfine = (uint32_t)sv.fine_nxy * (uint32_t)((sv.cells_height + 3) >> 2);
+	uint32_t nfine;
+	if (shift == 2) {  // the coarse bitmap's own grid: a pair's index is its block's bit index
+		sv.fine_nx = sv.coarse_roww * 32;
+		sv.fine_nxy = sv.fine_nx * sv.coarse_nby;
+		nfine = sv.coarse_words * 32;
+	} else {
+		const int bias = 1 << shift;
+		sv.fine_nx = (sv.cells + 2 * bias + 3) >> 2;
+		sv.fine_nxy = sv.fine_nx * sv.fine_nx;
+		nfine = (uint32_t)sv.fine_nxy * (uint32_t)((sv.cells_height + 2 * bias + 3) >> 2);
+	}
 	cudaFree(c->d_fine);
 	c->d_fine = nullptr;
 	CK(cudaMalloc(&c->d_fine, (size_t)nfine * 8));
