@@ -199,6 +199,11 @@ def main():
 
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
+    # NCCL prints its version banner to stdout when the communicator comes up (NCCL_DEBUG=VERSION on some boxes): keep stdout to
+    # the one JSON line by pointing fd 1 at stderr until the first collective is through
+    sys.stdout.flush()
+    saved_stdout = os.dup(1)
+    os.dup2(2, 1)
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
 
@@ -211,6 +216,10 @@ def main():
     ren.set_camera(bm.make_camera(position=CAM_POS, direction=CAM_DIR))
     exchange = RequestExchange(cfg.brick_load_queue_size, dev, world)
     exchange.exchange(ren)  # NCCL communicator warm-up outside the timed region
+    torch.cuda.synchronize(dev)
+    sys.stdout.flush()
+    os.dup2(saved_stdout, 1)
+    os.close(saved_stdout)
     blit = torch.zeros(rows, WIDTH, 4, dtype=torch.float32, device=dev)
     accum_host = torch.zeros(rows, WIDTH, 4, dtype=torch.float32).pin_memory()
     req_count_host = torch.zeros(1, dtype=torch.int32).pin_memory()

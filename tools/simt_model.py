@@ -115,7 +115,6 @@ def main():
         build()
     z = np.load(CACHE)
     occ, o, d, dist, kind = z["occ"], z["o"], z["d"], z["dist"], z["kind"]
-    SEQ = CACHE.replace(".npz", "_seq.npz")
     seq, nsteps = walk(occ, o, d, dist)
     print("rays %d (extend %d, shadow %d); mean cell tests per ray %.1f (extend %.1f, shadow %.1f)" % (
         len(o), (kind == 0).sum(), (kind == 1).sum(), nsteps.mean(), nsteps[kind == 0].mean(), nsteps[kind == 1].mean()))
