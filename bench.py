@@ -106,9 +106,18 @@ def cpu_baseline_port(frames=3):
         ren.frame(threads=0)
     dt = time.perf_counter() - t0
     rays = ren.stats.rays
+    # untimed: one more frame with the footprint instrumentation on -> minimum brick-index footprint (32 B x unique
+    # index-word and brick sectors the reference algorithm touches in the frame), the comparator of roofline.traffic
+    scene.footprint_begin()
+    ren.frame(threads=0)
+    fp = ob.Stats()
+    scene.footprint_report(fp)
+    fp_rays = ren.stats.rays - rays
     return {"value": rays / dt / 1e6, "unit": "Mrays/s", "cores": cores, "kind": "port",
             "sample": "first %d frames (%d rays) of the same workload; traversal multi-threaded over all cores, shade loop single-threaded (slot order)" % (frames, rays),
-            "seconds": dt}
+            "seconds": dt,
+            "min_footprint": {"bytes_per_frame": 32 * (fp.unique_index_sectors + fp.unique_brick_sectors), "bytes_per_ray": 32 * (fp.unique_index_sectors + fp.unique_brick_sectors) / max(fp_rays, 1),
+                              "frame": frames + 1, "note": "32 B x (unique index-word sectors + unique brick sectors) of one frame, from the oracle"}}
 
 
 def run_reference(args, rank, world):
@@ -333,6 +342,7 @@ def main():
                 "kernel": "frame_kernel_q", "peak_source": peak_kind + " (MEASURED_PEAKS.json hbm_gbs, torch copy)",
                 "algorithmic_bytes_per_ray": bytes_per_ray, "rays_per_launch": rays_per_launch, "kernel_ms_per_launch": kernel_ms / launches0,
                 "kernel_share_of_step": kernel_ms / ms if ms > 0 else None,
+                "traffic_bytes_per_ray": (traffic / rays_per_launch) if traffic else None,
                 "per_ray": {"cell_steps": work["cell_steps"] / max(wrays, 1), "index_words_loaded": work["index_reads"] / max(wrays, 1),
                             "bricks_entered": work["bricks_entered"] / max(wrays, 1)}}
     cpu = None if args.no_cpu_baseline else cpu_baseline_port()
