@@ -33,14 +33,18 @@ enum : int {
 	E_FLAGS,                // kind | (last stepped axis + 1) << 2 | cell position z << 4 (12 bits) | bounces << 16
 	E_CX, E_CY, E_CZ,       // throughput of an extend ray / colour of a shadow ray
 	E_PIXEL, E_SLOT,
-	E_WORDS
+	E_WORDS,                // entry size of the throughput instantiation
+	E_NX = E_WORDS, E_NY, E_NZ,  // RECORD only: the normal as extend has left it so far (part of the post-extend record of every slot;
+	                             // without RECORD a suspended ray's normal is dead: any later hit overwrites it, a miss does not use it)
+	E_WORDS_RECORD
 };
 enum : int { K_NONE = -1, K_EXTEND = 0, K_SHADOW = 1, K_SHADOW_NEW = 2 };
 
 #define QF(field, e) q[(field) * kQueueEntries + (e)]
 #define QU(field, e) reinterpret_cast<uint32_t*>(q)[(field) * kQueueEntries + (e)]
 
-template <bool STOCK>
+// RECORD (bm_launch_frame): additionally leaves the post-extend record of every slot and the shadow-ray records, like frame_kernel<RECORD>
+template <bool STOCK, bool RECORD>
 __global__ void __launch_bounds__(kQBlock, 1) frame_kernel_q(const FrameParams fp, const SceneView sv, const FrameIO io, const int quantum, const int min_share, const int descending, const int inline_tests) {
 	extern __shared__ uint32_t s_coarse[];
 	DeviceState* st = io.st;
@@ -54,7 +58,7 @@ __global__ void __launch_bounds__(kQBlock, 1) frame_kernel_q(const FrameParams f
 	const uint32_t frame = st->frame;
 	const uint32_t lane = threadIdx.x & 31;
 	const uint32_t lt_mask = (1u << lane) - 1u;
-	float* q = reinterpret_cast<float*>(s_coarse + sv.coarse_words) + (threadIdx.x >> 5) * (E_WORDS * kQueueEntries);
+	float* q = reinterpret_cast<float*>(s_coarse + sv.coarse_words) + (threadIdx.x >> 5) * ((RECORD ? E_WORDS_RECORD : E_WORDS) * kQueueEntries);
 	uint32_t qn = 0;  // entries in the warp's queue (warp-uniform)
 	uint32_t n_shadow = 0, n_term = 0, n_unocc = 0;
 
@@ -92,6 +96,7 @@ __global__ void __launch_bounds__(kQBlock, 1) frame_kernel_q(const FrameParams f
 				} else {
 					if (kind == K_EXTEND) {
 						slot = QU(E_SLOT, e);
+						if (RECORD) normal = F3{ QF(E_NX, e), QF(E_NY, e), QF(E_NZ, e) };
 					}
 					// the traversal state exactly as it was saved; tdelta and the integer steps as dda_setup derives them
 					ts.origin = F3{ QF(E_OX, e), QF(E_OY, e), QF(E_OZ, e) };
@@ -178,6 +183,7 @@ __global__ void __launch_bounds__(kQBlock, 1) frame_kernel_q(const FrameParams f
 				ray.identifier = 0;
 				ray.bounces = bounces;
 				ray.pixel_index = pixel;
+				if (RECORD) store_ray(io.record + slot, ray);  // what extend leaves in the work queue (kernel.cu:235-236)
 				const ShadeResult s = shade_vertex(fp, frame, slot, ray);
 				if (s.add_radiance) accum_add(io.accum, pixel, s.radiance.x, s.radiance.y, s.radiance.z, 1.f);
 				else if (s.terminated) accum_add(io.accum, pixel, 0.f, 0.f, 0.f, 1.f);
@@ -192,6 +198,10 @@ __global__ void __launch_bounds__(kQBlock, 1) frame_kernel_q(const FrameParams f
 					push_o = ray.origin;
 					push_d = s.shadow_dir;
 					push_c = s.shadow_color;
+					if (RECORD) {  // kernel.cu:277-278, sparse by slot like the survivors
+						store_shadow(io.shadow_out + slot, ray.origin, s.shadow_dir, s.shadow_color, pixel);
+						atomicOr(io.shadow_mask + (slot >> 5), 1u << (slot & 31));
+					}
 				}
 			}
 		}
@@ -224,7 +234,10 @@ __global__ void __launch_bounds__(kQBlock, 1) frame_kernel_q(const FrameParams f
 				QU(E_FLAGS, e) = (uint32_t)push | ((uint32_t)(ts.step_axis + 1) << 2) | ((uint32_t)ts.a.pos.z << 4) | ((uint32_t)bounces << 16);
 				QF(E_CX, e) = payload.x; QF(E_CY, e) = payload.y; QF(E_CZ, e) = payload.z;
 				QU(E_PIXEL, e) = pixel;
-				if (push == K_EXTEND) QU(E_SLOT, e) = slot;
+				if (push == K_EXTEND) {
+					QU(E_SLOT, e) = slot;
+					if (RECORD) { QF(E_NX, e) = normal.x; QF(E_NY, e) = normal.y; QF(E_NZ, e) = normal.z; }
+				}
 			}
 		}
 		qn += __popc(pm);

@@ -6,8 +6,9 @@
 //     on the way out (survivors only), as four 128-bit transactions. The reference moves ~310 B per slot through L2/HBM.
 //   * Two frame kernels with identical results. frame_kernel_q (bm_frame_quantum.cuh) is the throughput path of bm_render:
 //     a warp traces 32 rays at a time and suspends / regroups them through a work queue in shared memory, so that long rays
-//     do not hold 31 idle lanes. frame_kernel (below) keeps one thread on one slot from start to end; it serves
-//     bm_launch_frame (RECORD: every buffer the reference's kernels leave), the work counters (COUNT) and very large worlds.
+//     do not hold 31 idle lanes; its RECORD instantiation serves bm_launch_frame (every buffer the reference's kernels
+//     leave). frame_kernel (below) keeps one thread on one slot from start to end; it serves the work counters (COUNT) and
+//     worlds whose bitmap or queue entries do not fit the throughput kernel.
 //   * Warps pull runs of 128 consecutive slots with one atomic per run (the reference: one same-address atomic per ray per
 //     kernel, kernel.cu:158,228,245,330). Survivors are written sparse at their slot and flagged in a bitmask; a 1-block scan
 //     kernel turns the mask popcounts into the next frame's slot numbering (search + select in survivor_ptr), advances the
@@ -572,7 +573,7 @@ struct bm_context {
 	int descending = 0;       // BRICKMAP_B200_DESCENDING: hand out slot runs from the end of the frame
 	int q_blocks = 0;
 	bool q_stock = false;
-	size_t q_smem = 0;
+	size_t q_smem = 0, q_smem_record = 0;
 };
 
 static int props_smem_optin(int device) {
@@ -825,11 +826,14 @@ int bm_scene_bind(bm_context* c, bm_gpu_scene scene) {
 	c->q_stock = sv.coarse_shift == 2 && sv.coarse_nby == 130 && sv.coarse_roww == 5;  // the stock world's bitmap geometry is compiled in
 	if (const char* e = getenv("BRICKMAP_B200_NO_STOCK")) c->q_stock = c->q_stock && e[0] != '1';  // A/B switch for profiling
 	c->q_smem = (size_t)sv.coarse_words * 4 + (size_t)(kQBlock / 32) * E_WORDS * kQueueEntries * 4;
-	if (c->q_smem > (size_t)props_smem_optin(c->cfg.device)) c->use_quantum = false;
+	c->q_smem_record = (size_t)sv.coarse_words * 4 + (size_t)(kQBlock / 32) * E_WORDS_RECORD * kQueueEntries * 4;
+	if (c->q_smem_record > (size_t)props_smem_optin(c->cfg.device)) c->use_quantum = false;
 	if (c->use_quantum) {
-		CK(cudaFuncSetAttribute(frame_kernel_q<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)c->q_smem));
-		CK(cudaFuncSetAttribute(frame_kernel_q<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)c->q_smem));
-		CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, frame_kernel_q<false>, kQBlock, c->q_smem));
+		CK(cudaFuncSetAttribute(frame_kernel_q<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)c->q_smem));
+		CK(cudaFuncSetAttribute(frame_kernel_q<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)c->q_smem));
+		CK(cudaFuncSetAttribute(frame_kernel_q<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)c->q_smem_record));
+		CK(cudaFuncSetAttribute(frame_kernel_q<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)c->q_smem_record));
+		CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, frame_kernel_q<false, true>, kQBlock, c->q_smem_record));
 	}
 	if (per_sm < 1) c->use_quantum = false;
 	c->q_blocks = c->sm_count * (per_sm < 1 ? 1 : per_sm);
@@ -982,9 +986,13 @@ static int launch_frame_kernels(bm_context* c, const FrameIO& io, bool count) {
 		CK(cudaEventRecord(e0, c->stream));
 	}
 	if (count) frame_kernel<RECORD, true><<<blocks, kTile, c->frame_smem, c->stream>>>(c->fp, c->sv, io);
-	else if (RECORD || !c->use_quantum) frame_kernel<RECORD, false><<<blocks, kTile, c->frame_smem, c->stream>>>(c->fp, c->sv, io);
-	else if (c->q_stock) frame_kernel_q<true><<<c->q_blocks, kQBlock, c->q_smem, c->stream>>>(c->fp, c->sv, io, c->quantum, c->min_share, c->descending, c->inline_tests);
-	else frame_kernel_q<false><<<c->q_blocks, kQBlock, c->q_smem, c->stream>>>(c->fp, c->sv, io, c->quantum, c->min_share, c->descending, c->inline_tests);
+	else if (!c->use_quantum) frame_kernel<RECORD, false><<<blocks, kTile, c->frame_smem, c->stream>>>(c->fp, c->sv, io);
+	else {
+		const size_t smem = RECORD ? c->q_smem_record : c->q_smem;
+		if (RECORD) CK(cudaMemsetAsync(io.shadow_mask, 0, (size_t)c->ntiles * 32, c->stream));  // the kernel sets bits with atomicOr
+		if (c->q_stock) frame_kernel_q<true, RECORD><<<c->q_blocks, kQBlock, smem, c->stream>>>(c->fp, c->sv, io, c->quantum, c->min_share, c->descending, c->inline_tests);
+		else frame_kernel_q<false, RECORD><<<c->q_blocks, kQBlock, smem, c->stream>>>(c->fp, c->sv, io, c->quantum, c->min_share, c->descending, c->inline_tests);
+	}
 	CK(cudaGetLastError());
 	if (c->timing) CK(cudaEventRecord(e1, c->stream));
 	// the mask that was this frame's input becomes the next frame's output: the scan clears it
