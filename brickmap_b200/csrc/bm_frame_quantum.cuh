@@ -43,9 +43,20 @@ enum : int { K_NONE = -1, K_EXTEND = 0, K_SHADOW = 1, K_SHADOW_NEW = 2 };
 #define QF(field, e) q[(field) * kQueueEntries + (e)]
 #define QU(field, e) reinterpret_cast<uint32_t*>(q)[(field) * kQueueEntries + (e)]
 
+// Scheduling parameters of frame_kernel_q (none of them can change a result; defaults = measured best)
+struct QSched {
+	int quantum;       // cell tests a ray may take in one batch before it is suspended
+	int min_share;     // a batch is given up once fewer than min_share / 32 of the lanes that started tracing are left
+	int descending;    // hand out slot runs from the end of the frame
+	int inline_tests;  // bricks met after this many cell tests of a batch suspend the ray in front of the brick
+	int run_len;       // a warp pulls run_len * 32 consecutive slots per ticket
+	int resume_at;     // queued rays are resumed as soon as this many have piled up (<= 32)
+};
+
 // RECORD (bm_launch_frame): additionally leaves the post-extend record of every slot and the shadow-ray records, like frame_kernel<RECORD>
 template <bool STOCK, bool RECORD>
-__global__ void __launch_bounds__(kQBlock, 1) frame_kernel_q(const FrameParams fp, const SceneView sv, const FrameIO io, const int quantum, const int min_share, const int descending, const int inline_tests) {
+__global__ void __launch_bounds__(kQBlock, 1) frame_kernel_q(const FrameParams fp, const SceneView sv, const FrameIO io, const QSched sch) {
+	const int quantum = sch.quantum, min_share = sch.min_share, descending = sch.descending, inline_tests = sch.inline_tests;
 	extern __shared__ uint32_t s_coarse[];
 	DeviceState* st = io.st;
 	if (st->done) return;
@@ -62,7 +73,7 @@ __global__ void __launch_bounds__(kQBlock, 1) frame_kernel_q(const FrameParams f
 	uint32_t qn = 0;  // entries in the warp's queue (warp-uniform)
 	uint32_t n_shadow = 0, n_term = 0, n_unocc = 0;
 
-	constexpr uint32_t kRun = 4;  // warps pull runs of kRun * 32 consecutive slots with one atomic
+	const uint32_t kRun = (uint32_t)sch.run_len, resume_at = (uint32_t)sch.resume_at;  // warps pull runs of kRun * 32 consecutive slots with one atomic
 	const uint32_t nruns = (fp.n_slots + kRun * 32 - 1) / (kRun * 32);
 	uint32_t run = 0, round = kRun;
 	bool pool_dry = false;
@@ -77,7 +88,7 @@ __global__ void __launch_bounds__(kQBlock, 1) frame_kernel_q(const FrameParams f
 		uint32_t pixel = 0, slot = 0;
 		int bounces = 0;
 
-		if (qn >= 32 || (pool_dry && qn > 0)) {
+		if (qn >= resume_at || (pool_dry && qn > 0)) {
 			// ---- resume a batch of queued rays --------------------------------------------------------------------------
 			const uint32_t take = min(qn, 32u);
 			qn -= take;

@@ -142,9 +142,9 @@ __global__ void __launch_bounds__(kTile, 4) frame_kernel(const FrameParams fp, c
 	unsigned long long n_shadow = 0, n_term = 0, n_unocc = 0;
 	WorkCounters wc{ 0, 0, 0, 0 };
 
-	// each warp pulls runs of kRun * 32 consecutive slots with one atomic (the reference: one same-address atomic per ray per
+	// each warp pulls kRun * 32 consecutive slots with one atomic (the reference: one same-address atomic per ray per
 	// kernel, kernel.cu:158,228,245,330); no block-level synchronisation inside the frame
-	constexpr uint32_t kRun = 4;
+	constexpr uint32_t kRun = 1;  // one ticket per 32 slots: what a warp still holds when the pool runs dry is the frame's tail
 	const uint32_t lane = threadIdx.x & 31;
 	float* q = reinterpret_cast<float*>(s_coarse + sv.coarse_words) + (threadIdx.x >> 5) * (10 * kShadowQueue);  // this warp's shadow-ray queue
 	uint32_t qn = 0;                                                                                               // entries queued (warp-uniform)
@@ -570,6 +570,8 @@ struct bm_context {
 	int quantum = 256;        // BRICKMAP_B200_QUANTUM: cell tests per lane and batch at most (with min_share 16: 64 -> 2440, 128 -> 2478, 256 -> 2494 Mrays/s)
 	int min_share = 16;       // BRICKMAP_B200_MIN_SHARE: a batch is given up when fewer than min_share / 32 of its tracing lanes are left
 	int inline_tests = 0x7FFFFFFF;  // BRICKMAP_B200_INLINE_TESTS: bricks met after this many cell tests of a batch suspend the ray (trace_run)
+	int run_len = 1;          // BRICKMAP_B200_RUN_LEN (1: 2723, 2: 2666, 4: 2503, 8: 2215, 16: 1683 Mrays/s -- the runs a warp still holds when the pool runs dry are the frame's tail)
+	int resume_at = 32;       // BRICKMAP_B200_RESUME_AT
 	int descending = 0;       // BRICKMAP_B200_DESCENDING: hand out slot runs from the end of the frame
 	int q_blocks = 0;
 	bool q_stock = false;
@@ -820,6 +822,8 @@ int bm_scene_bind(bm_context* c, bm_gpu_scene scene) {
 	if (const char* e = getenv("BRICKMAP_B200_QUANTUM")) c->quantum = atoi(e) > 0 ? atoi(e) : c->quantum;
 	c->quantum = (c->quantum + kTraceChunk - 1) / kTraceChunk * kTraceChunk;
 	if (const char* e = getenv("BRICKMAP_B200_INLINE_TESTS")) c->inline_tests = atoi(e) > 0 ? atoi(e) : c->inline_tests;
+	if (const char* e = getenv("BRICKMAP_B200_RUN_LEN")) c->run_len = atoi(e) >= 1 && atoi(e) <= 64 ? atoi(e) : c->run_len;
+	if (const char* e = getenv("BRICKMAP_B200_RESUME_AT")) c->resume_at = atoi(e) >= 1 && atoi(e) <= 32 ? atoi(e) : c->resume_at;
 	if (const char* e = getenv("BRICKMAP_B200_DESCENDING")) c->descending = e[0] == '1';
 	if (const char* e = getenv("BRICKMAP_B200_MIN_SHARE")) c->min_share = atoi(e) >= 0 && atoi(e) <= 32 ? atoi(e) : c->min_share;
 	if (sv.cells + (2 << shift) > 65535 || sv.cells_height + (2 << shift) > 4095) c->use_quantum = false;  // queue entries pack the biased cell position into 16 + 16 + 12 bits
@@ -989,9 +993,10 @@ static int launch_frame_kernels(bm_context* c, const FrameIO& io, bool count) {
 	else if (!c->use_quantum) frame_kernel<RECORD, false><<<blocks, kTile, c->frame_smem, c->stream>>>(c->fp, c->sv, io);
 	else {
 		const size_t smem = RECORD ? c->q_smem_record : c->q_smem;
+		const QSched sch{ c->quantum, c->min_share, c->descending, c->inline_tests, c->run_len, c->resume_at };
 		if (RECORD) CK(cudaMemsetAsync(io.shadow_mask, 0, (size_t)c->ntiles * 32, c->stream));  // the kernel sets bits with atomicOr
-		if (c->q_stock) frame_kernel_q<true, RECORD><<<c->q_blocks, kQBlock, smem, c->stream>>>(c->fp, c->sv, io, c->quantum, c->min_share, c->descending, c->inline_tests);
-		else frame_kernel_q<false, RECORD><<<c->q_blocks, kQBlock, smem, c->stream>>>(c->fp, c->sv, io, c->quantum, c->min_share, c->descending, c->inline_tests);
+		if (c->q_stock) frame_kernel_q<true, RECORD><<<c->q_blocks, kQBlock, smem, c->stream>>>(c->fp, c->sv, io, sch);
+		else frame_kernel_q<false, RECORD><<<c->q_blocks, kQBlock, smem, c->stream>>>(c->fp, c->sv, io, sch);
 	}
 	CK(cudaGetLastError());
 	if (c->timing) CK(cudaEventRecord(e1, c->stream));

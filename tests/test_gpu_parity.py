@@ -289,8 +289,11 @@ def test_throughput_kernel_schedules_agree(golden, stores, variant, monkeypatch)
     cfg = store.cfg
     h, w = cfg.screen_height, cfg.screen_width
     results = []
-    for quantum, share, no_stock, inline, descending in ((64, 0, 0, 0, 0), (16, 0, 0, 0, 0), (256, 16, 0, 0, 0), (512, 28, 0, 0, 1), (256, 16, 1, 0, 0),
-                                                         (256, 16, 0, 1, 0), (128, 8, 0, 3, 1)):
+    for quantum, share, no_stock, inline, descending, run_len, resume_at in (
+            (64, 0, 0, 0, 0, 1, 32), (16, 0, 0, 0, 0, 4, 32), (256, 16, 0, 0, 0, 1, 32), (512, 28, 0, 0, 1, 2, 24), (256, 16, 1, 0, 0, 1, 32),
+            (256, 16, 0, 1, 0, 1, 32), (128, 8, 0, 3, 1, 16, 7)):
+        monkeypatch.setenv("BRICKMAP_B200_RUN_LEN", str(run_len))
+        monkeypatch.setenv("BRICKMAP_B200_RESUME_AT", str(resume_at))
         monkeypatch.setenv("BRICKMAP_B200_QUANTUM", str(quantum))
         monkeypatch.setenv("BRICKMAP_B200_MIN_SHARE", str(share))
         monkeypatch.setenv("BRICKMAP_B200_NO_STOCK", str(no_stock))
