@@ -1,13 +1,14 @@
 // frame_kernel_q: the throughput form of one frame. Same results as frame_kernel (bit for bit on everything geometric).
 //
 // Why: in frame_kernel a warp traces 32 rays until the LONGEST of them ends; on the benchmark workload that leaves 43 % of
-// the lanes busy (ray lengths: median 79 cell steps, 90th percentile 215, maximum 830). Here a lane traces for at most
-// `quantum` cell steps at a time. A ray that has not ended by then is SUSPENDED: its traversal state (position, tmax, axis --
-// tdelta and the step signs are recomputed from the direction) and its payload go into the warp's work queue in shared memory,
-// and the warp goes on with rays that are at the same stage: whenever 32 suspended rays have piled up they are resumed
-// together, otherwise the warp starts 32 fresh slots. Replaying the measured length distribution gives 76 % busy lanes at a
-// quantum of 64 and 86 % at 32. Shadow rays go through the same queue (they are born into it by shade), so they too are
-// traced 32 at a time and in quanta. Suspending never changes a result: the DDA state is saved and restored exactly.
+// the lanes busy (ray lengths: median 79 cell steps, 90th percentile 215, maximum 830). Here a warp traces a BATCH of 32 rays,
+// and a ray that has not ended is SUSPENDED when it has used its budget of `quantum` cell tests or -- the rule that fires in
+// practice -- as soon as fewer than min_share / 32 of the lanes that started the batch are still tracing. Its traversal state
+// (position, tmax, axis -- tdelta and the step signs are recomputed from the direction) and its payload go into the warp's
+// work queue in shared memory; whenever `resume_at` (32) suspended rays have piled up they are resumed together, otherwise
+// the warp takes a ticket for the next 32 fresh slots of the frame. Shadow rays go through the same queue (they are born
+// into it by shade), so they too are traced 32 at a time. Suspending never changes a result: the DDA state is saved and
+// restored exactly. Measured on the benchmark view: lanes active in the cell loop 13 -> 24 of 32.
 //
 // Only rays that start inside the world (tminn == 0, voxel.cuh:136-141) are ever suspended: for them the trace-space origin is
 // the world-space origin times 1/8 exactly, so the entry needs neither tminn nor the world-space origin that shading wants. A
@@ -23,7 +24,7 @@ namespace bm {
 #define BM_QBLOCK 1024
 #endif
 constexpr int kQBlock = BM_QBLOCK;  // 32 warps, one block per SM (shared memory: bitmap 46 KiB + 32 queues 128 KiB).
-                                    // Measured on the benchmark view: 512 threads 2.06, 768 2.35, 1024 2.49 Grays/s
+                                    // Measured on the benchmark view (128-slot tickets): 512 threads 2.06, 768 2.35, 1024 2.49 Grays/s
 constexpr int kQueueEntries = 64;
 enum : int {
 	E_OX = 0, E_OY, E_OZ,   // trace-space origin in cell units (continuations) / world-space origin (new shadow rays)
