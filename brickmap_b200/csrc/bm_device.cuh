@@ -268,10 +268,14 @@ __device__ __forceinline__ bool intersect_brick(const F3& origin, const F3& dire
 	a.pos = I3{ a.pos.x & 7, a.pos.y & 7, a.pos.z & 7 };
 	distance = 0.f;
 	int step_axis = -1;
-	const uint32_t* words = brick->data;
+	// The 64 bits of the z-slice the DDA stands in are kept in registers and reloaded only when z changes: two steps out of
+	// three test a bit without a load in their dependent chain (the walk runs with few lanes and is latency-bound).
+	const uint2* slices = reinterpret_cast<const uint2*>(brick->data);  // bricks are 64-byte aligned (Scene.cpp:170-176)
+	int cz = a.pos.z;
+	uint2 slice = __ldg(slices + cz);
 	for (;;) {
-		const int lin = a.pos.x + a.pos.y * 8 + a.pos.z * 64;
-		const uint32_t w = __ldg(words + (lin >> 5));
+		const int bit = a.pos.x + a.pos.y * 8;
+		const uint32_t w = (bit & 32) ? slice.y : slice.x;
 		uint32_t set;
 		asm("{\n\t"
 		    ".reg .b32 m;\n\t"
@@ -279,7 +283,7 @@ __device__ __forceinline__ bool intersect_brick(const F3& origin, const F3& dire
 		    "and.b32 %0, %2, m;\n\t"
 		    "}"
 		    : "=r"(set)
-		    : "r"(lin), "r"(w));
+		    : "r"(bit), "r"(w));
 		if (set) {
 			if (step_axis > -1) {
 				normal = axis_normal(a, step_axis);
@@ -288,6 +292,10 @@ __device__ __forceinline__ bool intersect_brick(const F3& origin, const F3& dire
 			return true;
 		}
 		if (!dda_advance(a, lim, step_axis)) break;
+		if (a.pos.z != cz) {
+			cz = a.pos.z;
+			slice = __ldg(slices + cz);
+		}
 	}
 	return false;
 }

@@ -46,7 +46,8 @@ typedef struct bm_shadow {
 	uint32_t pixel_index;
 } bm_shadow;
 
-/* Brick, Scene.h:3-5 (64 bytes): bit x + 8y + 64z of an 8x8x8 voxel block. */
+/* Brick, Scene.h:3-5 (64 bytes): bit x + 8y + 64z of an 8x8x8 voxel block. Brick arrays must be at least 8-byte aligned (the
+ * kernels read a z-slice as one 64-bit word); cudaMalloc'ed arrays of 64-byte bricks (Scene.cpp:170-176) are 64-byte aligned. */
 typedef struct bm_brick {
 	uint32_t data[16];
 } bm_brick;
