@@ -14,7 +14,7 @@ CSRC = os.path.join(HERE, "csrc")
 SOURCES = ["bm_kernels.cu", "bm_scene_store.cu"]
 HEADERS = ["bm_device.cuh", "bm_frame_quantum.cuh", os.path.join("..", "..", "include", "brickmap_b200.h")]
 LIB = os.path.join(HERE, "libbrickmap_b200.so")
-NVCC_FLAGS = (["-DBM_QDEBUG"] if os.environ.get("BM_QDEBUG") else []) + ["-std=c++17", "-O3", "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-fmad=false",
+NVCC_FLAGS = (["-DBM_QDEBUG"] if os.environ.get("BM_QDEBUG") else []) + ["-std=c++17", "-O3", "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-fmad=false", "-Xcompiler", "-ffp-contract=off",
               "-Xcompiler", "-fPIC", "-shared"]
 
 

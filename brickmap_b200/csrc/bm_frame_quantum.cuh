@@ -68,6 +68,8 @@ __global__ void __launch_bounds__(kQBlock, 1) frame_kernel_q(const FrameParams f
 	const uint32_t c = st->primary_ray_cnt;
 	const uint32_t start = st->start_position;
 	const uint32_t frame = st->frame;
+	const uint32_t cur = st->cur;
+	const uint32_t n_slots = st->n_active;
 	const uint32_t lane = threadIdx.x & 31;
 	const uint32_t lt_mask = (1u << lane) - 1u;
 	float* q = reinterpret_cast<float*>(s_coarse + sv.coarse_words) + (threadIdx.x >> 5) * ((RECORD ? E_WORDS_RECORD : E_WORDS) * kQueueEntries);
@@ -75,7 +77,7 @@ __global__ void __launch_bounds__(kQBlock, 1) frame_kernel_q(const FrameParams f
 	uint32_t n_shadow = 0, n_term = 0, n_unocc = 0;
 
 	const uint32_t kRun = (uint32_t)sch.run_len, resume_at = (uint32_t)sch.resume_at;  // warps pull runs of kRun * 32 consecutive slots with one atomic
-	const uint32_t nruns = (fp.n_slots + kRun * 32 - 1) / (kRun * 32);
+	const uint32_t nruns = (n_slots + kRun * 32 - 1) / (kRun * 32);
 	uint32_t run = 0, round = kRun;
 	bool pool_dry = false;
 
@@ -142,9 +144,9 @@ __global__ void __launch_bounds__(kQBlock, 1) frame_kernel_q(const FrameParams f
 			}
 			slot = (run * kRun + round) * 32 + lane;
 			round++;
-			if (slot < fp.n_slots) {
+			if (slot < n_slots) {
 				Ray ray;
-				if (slot < c) ray = load_ray(survivor_ptr(io, slot));
+				if (slot < c) ray = load_ray(survivor_ptr(input_set(io, cur), slot));
 				else ray = generate_primary(fp, frame, start, slot - c);  // primary_rays, kernel.cu:154-223
 				kind = K_EXTEND;
 				world = ray.origin;
@@ -196,13 +198,15 @@ __global__ void __launch_bounds__(kQBlock, 1) frame_kernel_q(const FrameParams f
 				ray.bounces = bounces;
 				ray.pixel_index = pixel;
 				if (RECORD) store_ray(io.record + slot, ray);  // what extend leaves in the work queue (kernel.cu:235-236)
-				const ShadeResult s = shade_vertex(fp, frame, slot, ray);
+				ShadeResult s;
+				if (RECORD && io.extend_only) s.has_shadow = s.survives = s.terminated = s.add_radiance = false;  // BM_FRAME_EXTEND_ONLY
+				else s = shade_vertex(fp, frame, slot, ray);
 				if (s.add_radiance) accum_add(io.accum, pixel, s.radiance.x, s.radiance.y, s.radiance.z, 1.f);
 				else if (s.terminated) accum_add(io.accum, pixel, 0.f, 0.f, 0.f, 1.f);
 				n_term += s.terminated;
 				if (s.survives) {
-					store_ray(io.out + slot, ray);
-					atomicOr(io.out_mask + (slot >> 5), 1u << (slot & 31));
+					store_ray(output_rays(io, cur) + slot, ray);
+					atomicOr(output_mask(io, cur) + (slot >> 5), 1u << (slot & 31));
 				}
 				if (s.has_shadow) {
 					n_shadow++;

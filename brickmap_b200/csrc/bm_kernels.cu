@@ -44,26 +44,41 @@ struct DeviceState {
 	uint32_t frame;            // kernel.cu:369
 	uint32_t tile_ticket;      // replaces raynr_primary/extend/shade/connect (kernel.cu:111-117)
 	uint32_t done;             // bm_render target reached
-	uint32_t pad0, pad1;
+	uint32_t cur;              // which private survivor set (FrameIO::rays/mask/prefix) holds the survivors of the last frame that RAN;
+	                           // toggled by scan_kernel, so frames the device skipped (done) do not move it
+	uint32_t n_active;         // slots of the NEXT frame: ray_queue_buffer_size, fewer only in the last frames of BM_FRAME_EXACT_PATHS
 	unsigned long long frames, extend_rays, shadow_rays, terminations, unoccluded, cell_steps, index_reads, bricks, requests;
 	unsigned long long paths_since_reset, target_paths;
+	uint32_t exact;            // BM_FRAME_EXACT_PATHS
+	uint32_t pad0;
 };
+
+// Slots of the next frame. Normally all N (the reference: every frame fills the queue, kernel.cu:160-163). BM_FRAME_EXACT_PATHS: only
+// as many fresh primaries as are still needed for `target` paths since the last reset -- every path started so far has either
+// finished (paths_since_reset) or is one of the c survivors, so target - paths_since_reset - c are still to be started.
+__device__ __forceinline__ uint32_t next_frame_slots(const DeviceState* st, uint32_t n_slots, uint32_t c) {
+	if (!st->exact || !st->target_paths) return n_slots;
+	const unsigned long long started = st->paths_since_reset + c;
+	const unsigned long long want = st->target_paths > started ? st->target_paths - started : 0ull;
+	const unsigned long long room = n_slots - c;
+	return c + (uint32_t)(want < room ? want : room);
+}
 
 struct FrameIO {
 	DeviceState* st;
-	// survivors of the previous frame. in_prefix == nullptr: dense records [0,c) (a caller's queue). Otherwise SPARSE: the
-	// survivor that came out of slot s of the previous frame sits at in[s], bit s of in_mask is set, and in_prefix[t] counts
-	// the survivors of slots < 256 t, so that survivor number k (= this frame's slot k) is found by search + select.
-	const bm_ray* in;
-	const uint32_t* in_mask;
-	const uint32_t* in_prefix;
-	bm_ray* out;             // survivors of this frame, sparse by slot
-	uint32_t* out_mask;      // 1 bit per slot (zero on entry)
+	// Two private survivor sets; set st->cur holds the survivors of the previous frame, the other one receives this frame's.
+	// A set is SPARSE: the survivor that came out of slot s sits at rays[s], bit s of mask is set, and prefix[t] counts the
+	// survivors of slots < 256 t, so that survivor number k (= the next frame's slot k) is found by search + select.
+	bm_ray* rays[2];
+	uint32_t* mask[2];       // 1 bit per slot (the output set's is zero on entry)
+	uint32_t* prefix[2];
+	const bm_ray* dense_in;  // != nullptr: the previous frame's survivors are the dense records [0,c) of a caller's queue instead
 	bm_ray* record;          // RECORD: the reference's work queue, post-extend record of every slot
 	bm_shadow* shadow_out;   // RECORD: shadow rays, sparse by slot
 	uint32_t* shadow_mask;   // RECORD
 	float4* accum;           // blit_buffer (state.h:22)
 	uint32_t ntiles;
+	uint32_t extend_only;    // BM_FRAME_EXTEND_ONLY: stop after extend (kernel.cu:416-418), nothing is shaded
 };
 
 __device__ __forceinline__ void accum_add(float4* accum, uint32_t pixel, float r, float g, float b, float a) {
@@ -73,7 +88,21 @@ __device__ __forceinline__ void accum_add(float4* accum, uint32_t pixel, float r
 
 // Where is survivor number `k` of the previous frame? Stable compaction = the reference's atomicAdd(&primary_ray_cnt, 1)
 // (kernel.cu:298-299) with the schedule fixed to slot order; the records themselves are never moved.
-__device__ __forceinline__ const bm_ray* survivor_ptr(const FrameIO& io, uint32_t k) {
+struct SurvivorSet {
+	const bm_ray* in;
+	const uint32_t* in_mask;
+	const uint32_t* in_prefix;  // nullptr: dense
+	uint32_t ntiles;
+};
+// (selects between kernel parameters at the point of use instead of indexing them: the pointers stay in the constant bank and
+// only `cur` lives in a register across the frame)
+__device__ __forceinline__ SurvivorSet input_set(const FrameIO& io, uint32_t cur) {
+	if (io.dense_in) return SurvivorSet{ io.dense_in, nullptr, nullptr, io.ntiles };
+	return cur ? SurvivorSet{ io.rays[1], io.mask[1], io.prefix[1], io.ntiles } : SurvivorSet{ io.rays[0], io.mask[0], io.prefix[0], io.ntiles };
+}
+__device__ __forceinline__ bm_ray* output_rays(const FrameIO& io, uint32_t cur) { return cur ? io.rays[0] : io.rays[1]; }
+__device__ __forceinline__ uint32_t* output_mask(const FrameIO& io, uint32_t cur) { return cur ? io.mask[0] : io.mask[1]; }
+__device__ __forceinline__ const bm_ray* survivor_ptr(const SurvivorSet& io, uint32_t k) {
 	if (!io.in_prefix) return io.in + k;
 	uint32_t lo = 0, hi = io.ntiles;  // tile t = max{ t : prefix[t] <= k }
 	while (hi - lo > 1) {
@@ -139,6 +168,8 @@ __global__ void __launch_bounds__(kTile, 4) frame_kernel(const FrameParams fp, c
 	const uint32_t c = st->primary_ray_cnt;
 	const uint32_t start = st->start_position;
 	const uint32_t frame = st->frame;
+	const uint32_t cur = st->cur;
+	const uint32_t n_slots = st->n_active;
 	unsigned long long n_shadow = 0, n_term = 0, n_unocc = 0;
 	WorkCounters wc{ 0, 0, 0, 0 };
 
@@ -148,7 +179,7 @@ __global__ void __launch_bounds__(kTile, 4) frame_kernel(const FrameParams fp, c
 	const uint32_t lane = threadIdx.x & 31;
 	float* q = reinterpret_cast<float*>(s_coarse + sv.coarse_words) + (threadIdx.x >> 5) * (10 * kShadowQueue);  // this warp's shadow-ray queue
 	uint32_t qn = 0;                                                                                               // entries queued (warp-uniform)
-	const uint32_t nruns = (fp.n_slots + kRun * 32 - 1) / (kRun * 32);
+	const uint32_t nruns = (n_slots + kRun * 32 - 1) / (kRun * 32);
 	uint32_t run = 0, round = kRun;
 	for (;;) {
 		if (round == kRun) {
@@ -159,27 +190,29 @@ __global__ void __launch_bounds__(kTile, 4) frame_kernel(const FrameParams fp, c
 		}
 		const uint32_t slot = (run * kRun + round) * 32 + lane;
 		round++;
-		if (slot - lane >= fp.n_slots) continue;
-		const bool valid = slot < fp.n_slots;
+		if (slot - lane >= n_slots) continue;
+		const bool valid = slot < n_slots;
 		Ray ray;
 		bool survives = false, has_shadow = false;
 		F3 shadow_dir{ 0, 0, 0 }, shadow_color{ 0, 0, 0 };
 		if (valid) {
-			if (slot < c) ray = load_ray(survivor_ptr(io, slot));
+			if (slot < c) ray = load_ray(survivor_ptr(input_set(io, cur), slot));
 			else ray = generate_primary(fp, frame, start, slot - c);  // primary_rays, kernel.cu:154-223
 			// extend, kernel.cu:226-238
 			ray.distance = kVeryFar;
 			intersect_voxel<COUNT>(sv, coarse, ray.origin, ray.direction, ray.normal, ray.distance, fp.cam_cell, &wc);
 			if (RECORD) store_ray(io.record + slot, ray);
-			// shade, kernel.cu:242-325
-			const ShadeResult s = shade_vertex(fp, frame, slot, ray);
-			survives = s.survives;
-			has_shadow = s.has_shadow;
-			shadow_dir = s.shadow_dir;
-			shadow_color = s.shadow_color;
-			if (s.add_radiance) accum_add(io.accum, ray.pixel_index, s.radiance.x, s.radiance.y, s.radiance.z, 1.f);
-			else if (s.terminated) accum_add(io.accum, ray.pixel_index, 0.f, 0.f, 0.f, 1.f);
-			n_term += s.terminated;
+			if (!io.extend_only) {
+				// shade, kernel.cu:242-325
+				const ShadeResult s = shade_vertex(fp, frame, slot, ray);
+				survives = s.survives;
+				has_shadow = s.has_shadow;
+				shadow_dir = s.shadow_dir;
+				shadow_color = s.shadow_color;
+				if (s.add_radiance) accum_add(io.accum, ray.pixel_index, s.radiance.x, s.radiance.y, s.radiance.z, 1.f);
+				else if (s.terminated) accum_add(io.accum, ray.pixel_index, 0.f, 0.f, 0.f, 1.f);
+				n_term += s.terminated;
+			}
 		}
 		// connect, kernel.cu:328-346. Only about half of the lanes come out of shade with a shadow ray, so the rays are queued
 		// per warp in shared memory and traced 32 at a time: the shadow traversal always runs with a full warp. (Which thread
@@ -202,9 +235,9 @@ __global__ void __launch_bounds__(kTile, 4) frame_kernel(const FrameParams fp, c
 				__syncwarp();
 			}
 		}
-		if (survives) store_ray(io.out + slot, ray);
+		if (survives) store_ray(output_rays(io, cur) + slot, ray);
 		const uint32_t smask = __ballot_sync(0xFFFFFFFFu, survives);
-		if (lane == 0) io.out_mask[slot >> 5] = smask;
+		if (lane == 0) output_mask(io, cur)[slot >> 5] = smask;
 		if (RECORD) {
 			if (has_shadow) store_shadow(io.shadow_out + slot, ray.origin, shadow_dir, shadow_color, ray.pixel_index);
 			const uint32_t hmask = __ballot_sync(0xFFFFFFFFu, has_shadow);
@@ -245,10 +278,16 @@ namespace bm {
 // set_wavefront_globals (kernel.cu:122-139) + per-tile survivor counts (popcount of the slot masks) -> exclusive prefix.
 // One block. mask[ntiles * 8] -> prefix[ntiles + 1]; optional second pair for the shadow queue (RECORD). Also zeroes
 // `clear_mask`, the mask buffer the NEXT frame will write with atomicOr.
-__global__ void __launch_bounds__(1024) scan_kernel(DeviceState* st, const uint32_t* mask, uint32_t* prefix, const uint32_t* shadow_mask, uint32_t* shadow_prefix,
-                                                     uint32_t* clear_mask, uint32_t ntiles, uint32_t n_slots, uint32_t pixels) {
+__global__ void __launch_bounds__(1024) scan_kernel(const FrameIO io, const uint32_t* shadow_mask, uint32_t* shadow_prefix, uint32_t ntiles, uint32_t n_slots,
+                                                     uint32_t pixels) {
 	__shared__ uint32_t s_part[1024];
+	DeviceState* st = io.st;
 	if (st->done) return;
+	const uint32_t cur = st->cur;  // the set the frame kernel read; it wrote set cur ^ 1
+	const uint32_t* mask = cur ? io.mask[0] : io.mask[1];
+	uint32_t* prefix = cur ? io.prefix[0] : io.prefix[1];
+	uint32_t* clear_mask = cur ? io.mask[1] : io.mask[0];  // this frame's input becomes the next frame's output
+	__syncthreads();  // every thread has read st->cur before thread 0 toggles it below
 	const uint32_t per = (ntiles + blockDim.x - 1) / blockDim.x;
 	for (int pass = 0; pass < 2; pass++) {
 		const uint32_t* in = pass == 0 ? mask : shadow_mask;
@@ -279,34 +318,48 @@ __global__ void __launch_bounds__(1024) scan_kernel(DeviceState* st, const uint3
 		if (threadIdx.x == 0) {
 			out[ntiles] = total;
 			if (pass == 0) {
-				const uint32_t progress = n_slots - st->primary_ray_cnt;  // kernel.cu:125
+				const uint32_t ran = st->n_active;                    // slots of the frame that just ran (n_slots unless BM_FRAME_EXACT_PATHS)
+				const uint32_t progress = ran - st->primary_ray_cnt;  // kernel.cu:125
 				st->start_position = (st->start_position + progress) % pixels;  // kernel.cu:130-131
 				st->primary_ray_cnt = total;  // survivors written by shade (kernel.cu:298)
 				st->frame += 1;               // kernel.cu:423
 				st->tile_ticket = 0;
+				st->cur = cur ^ 1;
 				st->frames += 1;
-				st->extend_rays += n_slots;
+				st->extend_rays += ran;
 				if (st->target_paths && st->paths_since_reset >= st->target_paths) st->done = 1;
+				st->n_active = next_frame_slots(st, n_slots, total);
 			} else {
 				st->shadow_ray_cnt = total;
 			}
 		}
 		__syncthreads();
 	}
-	if (clear_mask)
-		for (uint32_t i = threadIdx.x; i < ntiles * 2; i += blockDim.x) reinterpret_cast<uint4*>(clear_mask)[i] = make_uint4(0, 0, 0, 0);
+	for (uint32_t i = threadIdx.x; i < ntiles * 2; i += blockDim.x) reinterpret_cast<uint4*>(clear_mask)[i] = make_uint4(0, 0, 0, 0);
 }
 
 // start of a bm_render / bm_launch_frame call: install the stop target; a target that is already met stops at once
-__global__ void begin_kernel(DeviceState* st, unsigned long long target_paths) {
+__global__ void begin_kernel(DeviceState* st, unsigned long long target_paths, uint32_t exact, uint32_t n_slots) {
 	st->target_paths = target_paths;
+	st->exact = exact;
 	st->done = (target_paths && st->paths_since_reset >= target_paths) ? 1u : 0u;
 	st->tile_ticket = 0;
+	st->n_active = next_frame_slots(st, n_slots, st->primary_ray_cnt);
 }
 
 // sparse-by-slot -> dense (the layout the reference's queues have): dst[prefix[t] + rank of slot within tile t] = src[slot]
 template <typename T>
-__global__ void __launch_bounds__(kTile) export_kernel(const T* src, const uint32_t* mask, const uint32_t* prefix, T* dst, uint32_t ntiles) {
+__device__ __forceinline__ void export_tile(const T* src, const uint32_t* mask, const uint32_t* prefix, T* dst, uint32_t ntiles);
+// the private survivor set the last executed frame wrote (st->cur, see scan_kernel)
+__global__ void __launch_bounds__(kTile) export_rays_kernel(const FrameIO io, bm_ray* dst) {
+	const bool one = io.st->cur != 0;  // (never io.dense_in: that is the INPUT of a frame whose survivors are exported here)
+	export_tile<bm_ray>(one ? io.rays[1] : io.rays[0], one ? io.mask[1] : io.mask[0], one ? io.prefix[1] : io.prefix[0], dst, io.ntiles);
+}
+__global__ void __launch_bounds__(kTile) export_shadow_kernel(const bm_shadow* src, const uint32_t* mask, const uint32_t* prefix, bm_shadow* dst, uint32_t ntiles) {
+	export_tile<bm_shadow>(src, mask, prefix, dst, ntiles);
+}
+template <typename T>
+__device__ __forceinline__ void export_tile(const T* src, const uint32_t* mask, const uint32_t* prefix, T* dst, uint32_t ntiles) {
 	const uint32_t tile = blockIdx.x;
 	if (tile >= ntiles) return;
 	const uint32_t* m = mask + (size_t)tile * (kTile / 32);
@@ -540,8 +593,8 @@ struct bm_context {
 	bm_shadow* d_shadow = nullptr;  // RECORD scratch (sparse by slot)
 	uint32_t* d_shadow_mask = nullptr;
 	uint32_t* d_shadow_prefix = nullptr;
-	int cur = 0;                 // which private buffer holds the survivors of the last frame
-	bool private_valid = false;  // survivors of the last frame are in d_rays[cur] (tile-local)
+	bool private_valid = false;  // survivors of the last frame are in the private set DeviceState::cur (tile-local)
+	uint32_t caller_survivors = 0;  // primary_ray_cnt installed by bm_set_counters and not yet backed by records
 	// scene
 	bool bound = false;
 	bm_gpu_scene scene{};
@@ -881,6 +934,7 @@ int bm_set_counters(bm_context* c, const bm_counters* in) {
 	const uint32_t v[4] = { in->primary_ray_cnt, in->start_position, in->shadow_ray_cnt, in->frame };
 	CK(cudaMemcpy(c->d_state, v, sizeof(v), cudaMemcpyHostToDevice));
 	c->private_valid = false;  // the caller now owns the meaning of the survivor set (dense `queue`)
+	c->caller_survivors = in->primary_ray_cnt;
 	return 0;
 }
 
@@ -970,6 +1024,29 @@ static int drain_events(bm_context* c) {
 	return 0;
 }
 
+static FrameIO private_io(bm_context* c, float* blit) {
+	FrameIO io{};
+	io.st = c->d_state;
+	for (int i = 0; i < 2; i++) {
+		io.rays[i] = c->d_rays[i];
+		io.mask[i] = c->d_mask[i];
+		io.prefix[i] = c->d_prefix[i];
+	}
+	io.accum = reinterpret_cast<float4*>(blit);
+	io.ntiles = c->ntiles;
+	return io;
+}
+
+// no private survivor set (first frame, or after bm_set_counters without records): both sets empty, set 0 current
+static int clear_private_sets(bm_context* c) {
+	for (int i = 0; i < 2; i++) {
+		CK(cudaMemsetAsync(c->d_prefix[i], 0, (size_t)(c->ntiles + 1) * 4, c->stream));
+		CK(cudaMemsetAsync(c->d_mask[i], 0, (size_t)c->ntiles * 32, c->stream));
+	}
+	CK(cudaMemsetAsync(&c->d_state->cur, 0, 4, c->stream));
+	return 0;
+}
+
 template <bool RECORD>
 static int launch_frame_kernels(bm_context* c, const FrameIO& io, bool count) {
 	const int blocks = (int)(c->ntiles < (uint32_t)c->frame_blocks ? c->ntiles : (uint32_t)c->frame_blocks);
@@ -1000,9 +1077,10 @@ static int launch_frame_kernels(bm_context* c, const FrameIO& io, bool count) {
 	}
 	CK(cudaGetLastError());
 	if (c->timing) CK(cudaEventRecord(e1, c->stream));
-	// the mask that was this frame's input becomes the next frame's output: the scan clears it
-	scan_kernel<<<1, 1024, 0, c->stream>>>(c->d_state, io.out_mask, c->d_prefix[c->cur ^ 1], RECORD ? io.shadow_mask : nullptr,
-	                                       RECORD ? c->d_shadow_prefix : nullptr, c->d_mask[c->cur], c->ntiles, c->cfg.ray_queue_buffer_size, c->tile_pixels);
+	// counts the survivors, advances the cursor, toggles DeviceState::cur; the mask that was this frame's input becomes the next
+	// frame's output: the scan clears it
+	scan_kernel<<<1, 1024, 0, c->stream>>>(io, RECORD ? io.shadow_mask : nullptr, RECORD ? c->d_shadow_prefix : nullptr, c->ntiles, c->cfg.ray_queue_buffer_size,
+	                                       c->tile_pixels);
 	CK(cudaGetLastError());
 	c->launches += 2;
 	return 0;
@@ -1021,37 +1099,29 @@ int bm_launch_frame(bm_context* c, float* blit, bm_ray* queue, bm_ray* queue2, b
 		rc = launch_upload(c);
 		if (rc) return rc;
 	}
-	begin_kernel<<<1, 1, 0, c->stream>>>(c->d_state, 0ull);
+	begin_kernel<<<1, 1, 0, c->stream>>>(c->d_state, 0ull, 0u, c->cfg.ray_queue_buffer_size);
 	CK(cudaGetLastError());
 	c->launches += 1;
-	FrameIO io{};
-	io.st = c->d_state;
-	if (c->private_valid) {
-		// survivors of the previous frame are still in the private tile-local buffer; the caller's swapped `queue`
-		// holds the same records densely (main.cpp:146) and is not needed
-		io.in = c->d_rays[c->cur];
-		io.in_mask = c->d_mask[c->cur];
-		io.in_prefix = c->d_prefix[c->cur];
-	} else {
-		io.in = queue;  // dense survivors [0, primary_ray_cnt) supplied by the caller (after bm_set_counters)
-		io.in_mask = nullptr;
-		io.in_prefix = nullptr;
+	FrameIO io = private_io(c, blit);
+	if (!c->private_valid) {
+		// dense survivors [0, primary_ray_cnt) supplied by the caller in `queue` (after bm_set_counters); otherwise the survivors
+		// of the previous frame are still in the private set and the caller's swapped `queue` (main.cpp:146) is not needed
+		rc = clear_private_sets(c);
+		if (rc) return rc;
+		io.dense_in = queue;
 	}
-	io.out = c->d_rays[c->cur ^ 1];
-	io.out_mask = c->d_mask[c->cur ^ 1];
 	io.record = queue;
 	io.shadow_out = c->d_shadow;
 	io.shadow_mask = c->d_shadow_mask;
-	io.accum = reinterpret_cast<float4*>(blit);
-	io.ntiles = c->ntiles;
+	io.extend_only = (flags & BM_FRAME_EXTEND_ONLY) ? 1u : 0u;
 	rc = launch_frame_kernels<true>(c, io, (flags & BM_FRAME_COUNT_WORK) != 0);
 	if (rc) return rc;
-	c->cur ^= 1;
-	export_kernel<bm_ray><<<c->ntiles, kTile, 0, c->stream>>>(c->d_rays[c->cur], c->d_mask[c->cur], c->d_prefix[c->cur], queue2, c->ntiles);
+	export_rays_kernel<<<c->ntiles, kTile, 0, c->stream>>>(io, queue2);
 	CK(cudaGetLastError());
-	export_kernel<bm_shadow><<<c->ntiles, kTile, 0, c->stream>>>(c->d_shadow, c->d_shadow_mask, c->d_shadow_prefix, shadow_queue, c->ntiles);
+	export_shadow_kernel<<<c->ntiles, kTile, 0, c->stream>>>(c->d_shadow, c->d_shadow_mask, c->d_shadow_prefix, shadow_queue, c->ntiles);
 	CK(cudaGetLastError());
 	c->launches += 2;
+	c->caller_survivors = 0;
 	c->private_valid = true;
 	CK(cudaStreamSynchronize(c->stream));  // kernel.cu:431
 	return 0;
@@ -1060,37 +1130,32 @@ int bm_launch_frame(bm_context* c, float* blit, bm_ray* queue, bm_ray* queue2, b
 int bm_render(bm_context* c, float* blit, uint32_t frames, uint64_t target_paths, uint32_t flags, int sync) {
 	if (!c || !blit) return fail_api(BM_E_INVALID, "bm_render: null argument");
 	if (!c->bound) return fail_api(BM_E_STATE, "bm_render: no scene bound (bm_scene_bind)");
+	if (!c->private_valid && c->caller_survivors)
+		return fail_api(BM_E_STATE, "bm_render: bm_set_counters installed primary_ray_cnt > 0 without records (bm_import_rays, or use bm_launch_frame)");
 	CK(cudaSetDevice(c->cfg.device));
 	int rc = maybe_reset(c, blit, flags);
 	if (rc) return rc;
-	begin_kernel<<<1, 1, 0, c->stream>>>(c->d_state, (unsigned long long)target_paths);
+	if ((flags & BM_FRAME_EXACT_PATHS) && !target_paths) return fail_api(BM_E_INVALID, "bm_render: BM_FRAME_EXACT_PATHS needs target_paths");
+	begin_kernel<<<1, 1, 0, c->stream>>>(c->d_state, (unsigned long long)target_paths, (flags & BM_FRAME_EXACT_PATHS) ? 1u : 0u, c->cfg.ray_queue_buffer_size);
 	CK(cudaGetLastError());
 	c->launches += 1;
 	if (!c->private_valid) {
 		// no private survivor set (first frame, or the counters were set by the caller): start from an empty one
 		CK(cudaMemsetAsync(&c->d_state->primary_ray_cnt, 0, 4, c->stream));
-		CK(cudaMemsetAsync(c->d_prefix[c->cur], 0, (size_t)(c->ntiles + 1) * 4, c->stream));
-		CK(cudaMemsetAsync(c->d_mask[c->cur], 0, (size_t)c->ntiles * 32, c->stream));
-		CK(cudaMemsetAsync(c->d_mask[c->cur ^ 1], 0, (size_t)c->ntiles * 32, c->stream));
+		rc = clear_private_sets(c);
+		if (rc) return rc;
 		c->private_valid = true;
 	}
+	const FrameIO io = private_io(c, blit);
 	for (uint32_t f = 0; f < frames; f++) {
-		if (!(flags & BM_FRAME_NO_UPLOAD) && c->scene.bricks_queue && c->scene.indices_queue) {
+		// at most one batch of staged bricks exists per call (the host stages between calls, Scene.cpp:200-229): the upload step
+		// (kernel.cu:407-414) runs before the first frame only; later frames of the call append new requests to the emptied queue
+		if (f == 0 && !(flags & BM_FRAME_NO_UPLOAD) && c->scene.bricks_queue && c->scene.indices_queue) {
 			rc = launch_upload(c);
 			if (rc) return rc;
 		}
-		FrameIO io{};
-		io.st = c->d_state;
-		io.in = c->d_rays[c->cur];
-		io.in_mask = c->d_mask[c->cur];
-		io.in_prefix = c->d_prefix[c->cur];
-		io.out = c->d_rays[c->cur ^ 1];
-		io.out_mask = c->d_mask[c->cur ^ 1];
-		io.accum = reinterpret_cast<float4*>(blit);
-		io.ntiles = c->ntiles;
 		rc = launch_frame_kernels<false>(c, io, (flags & BM_FRAME_COUNT_WORK) != 0);
 		if (rc) return rc;
-		c->cur ^= 1;
 	}
 	if (sync) CK(cudaStreamSynchronize(c->stream));
 	return 0;
@@ -1099,11 +1164,13 @@ int bm_render(bm_context* c, float* blit, uint32_t frames, uint64_t target_paths
 int bm_import_rays(bm_context* c, const bm_ray* queue, uint32_t count) {
 	if (!c || (count && !queue) || count > c->cfg.ray_queue_buffer_size) return fail_api(BM_E_INVALID, "bm_import_rays: bad argument");
 	CK(cudaSetDevice(c->cfg.device));
-	if (count) CK(cudaMemcpyAsync(c->d_rays[c->cur], queue, (size_t)count * sizeof(bm_ray), cudaMemcpyDeviceToDevice, c->stream));
-	import_masks_kernel<<<(c->ntiles * 8 + 256) / 256, 256, 0, c->stream>>>(c->d_mask[c->cur], c->d_prefix[c->cur], c->ntiles, count);
+	if (count) CK(cudaMemcpyAsync(c->d_rays[0], queue, (size_t)count * sizeof(bm_ray), cudaMemcpyDeviceToDevice, c->stream));
+	import_masks_kernel<<<(c->ntiles * 8 + 256) / 256, 256, 0, c->stream>>>(c->d_mask[0], c->d_prefix[0], c->ntiles, count);
 	CK(cudaGetLastError());
-	CK(cudaMemsetAsync(c->d_mask[c->cur ^ 1], 0, (size_t)c->ntiles * 32, c->stream));
-	CK(cudaMemcpyAsync(&c->d_state->primary_ray_cnt, &c->d_prefix[c->cur][c->ntiles], 4, cudaMemcpyDeviceToDevice, c->stream));
+	CK(cudaMemsetAsync(c->d_mask[1], 0, (size_t)c->ntiles * 32, c->stream));
+	CK(cudaMemsetAsync(&c->d_state->cur, 0, 4, c->stream));
+	CK(cudaMemcpyAsync(&c->d_state->primary_ray_cnt, &c->d_prefix[0][c->ntiles], 4, cudaMemcpyDeviceToDevice, c->stream));
+	c->caller_survivors = 0;
 	c->launches += 1;
 	c->private_valid = true;
 	return 0;
@@ -1113,7 +1180,7 @@ int bm_export_rays(bm_context* c, bm_ray* queue2) {
 	if (!c || !queue2) return fail_api(BM_E_INVALID, "bm_export_rays: null argument");
 	if (!c->private_valid) return fail_api(BM_E_STATE, "bm_export_rays: no private survivor set");
 	CK(cudaSetDevice(c->cfg.device));
-	export_kernel<bm_ray><<<c->ntiles, kTile, 0, c->stream>>>(c->d_rays[c->cur], c->d_mask[c->cur], c->d_prefix[c->cur], queue2, c->ntiles);
+	export_rays_kernel<<<c->ntiles, kTile, 0, c->stream>>>(private_io(c, nullptr), queue2);
 	CK(cudaGetLastError());
 	c->launches += 1;
 	CK(cudaStreamSynchronize(c->stream));

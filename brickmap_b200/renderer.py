@@ -12,7 +12,7 @@ RAY_DTYPE = np.dtype([("origin", "<f4", 3), ("direction", "<f4", 3), ("throughpu
                       ("distance", "<f4"), ("identifier", "<i4"), ("bounces", "<i4"), ("pixel_index", "<u4")])
 SHADOW_DTYPE = np.dtype([("origin", "<f4", 3), ("direction", "<f4", 3), ("color", "<f4", 3), ("pixel_index", "<u4")])
 
-FRAME_DEFAULT, FRAME_NO_UPLOAD, FRAME_NO_RESET, FRAME_COUNT_WORK = 0, 1, 2, 4
+FRAME_DEFAULT, FRAME_NO_UPLOAD, FRAME_NO_RESET, FRAME_COUNT_WORK, FRAME_EXACT_PATHS, FRAME_EXTEND_ONLY = 0, 1, 2, 4, 8, 16
 SCENE_TERRAIN, SCENE_CAVES, SCENE_NONFLAT = 0, 1, 0x100
 
 

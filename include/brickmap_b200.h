@@ -82,7 +82,12 @@ typedef struct bm_config {
 	uint32_t screen_width, screen_height; /* full image (state.h:13-14) */
 	/* Image tile rendered by this context (multi-GPU partition, not in the reference): rows
 	 * [tile_row0, tile_row0 + tile_rows) of the full image. tile_rows == 0 means the whole image. The
-	 * accumulation buffer handed to bm_* then covers only the tile (tile_rows * screen_width pixels). */
+	 * accumulation buffer handed to bm_* then covers only the tile (tile_rows * screen_width pixels).
+	 * A tile is an INDEPENDENT renderer of its rows: the pixel cursor wraps inside the tile and RayQueue.pixel_index is the index
+	 * into the tile's own buffer (row_in_tile * width + x), which also feeds shade's seed (kernel.cu:252). Only the camera mapping
+	 * uses the full image (kernel.cu:183-184 with the full-image row). A tiled render is therefore a different random sequence
+	 * from the single-context render of the same image (same estimator, other samples); it equals, bit for bit, the reference
+	 * algorithm run with the same row mapping (the CPU oracle's tile mode, tests/test_gpu_parity.py). */
 	uint32_t tile_row0, tile_rows;
 	/* Interleaved partition (better load balance than one contiguous band: sky rows finish their paths after one segment,
 	 * terrain rows need up to four). strip_rows != 0: the image is cut into strips of strip_rows rows and this context owns
@@ -152,6 +157,13 @@ int bm_reset_stats(bm_context* ctx);
 #define BM_FRAME_NO_UPLOAD 1u   /* skip the staged-brick upload step (kernel.cu:407-414) */
 #define BM_FRAME_NO_RESET 2u    /* never reset the accumulation buffer on camera/sun change */
 #define BM_FRAME_COUNT_WORK 4u  /* fill the traversal work counters of bm_stats (slower) */
+#define BM_FRAME_EXACT_PATHS 8u /* bm_render with target_paths: start exactly target_paths paths since the last reset -- a frame only
+                                   takes as many fresh primaries as are still missing (the last frames shrink to the survivors), so
+                                   with target = spp * tile pixels every pixel gets exactly spp paths and no ray is traced beyond them.
+                                   Per-slot results are those of the reference algorithm run with the same per-frame slot counts. */
+#define BM_FRAME_EXTEND_ONLY 16u /* bm_launch_frame: stop after extend (primary_rays, set_wavefront_globals, extend: kernel.cu:416-418).
+                                   `queue` holds the post-extend record of every slot; nothing is shaded, no survivors, no shadow
+                                   rays, the accumulation buffer is untouched; cursor and frame number advance as usual. */
 
 /* One frame with the reference's buffer contract (launch_kernels, kernel.cu:366-439, minus the display blit):
  *   - applies the pending staged bricks and zeroes *brick_load_queue_count (kernel.cu:407-414),
@@ -168,7 +180,13 @@ int bm_launch_frame(bm_context* ctx, float* blit_buffer_device, bm_ray* queue_de
 /* Throughput path: `frames` consecutive frames with exactly the per-frame semantics above (same slots, seeds
  * and stable compaction order), but the ray and shadow state stay in library-private buffers and no
  * per-stage records are written. Stops early once `target_paths` paths have finished since the last
- * accumulation reset (0 = no target). Asynchronous on the context's stream unless `sync` is set. */
+ * accumulation reset (0 = no target); frames the device skips that way leave every piece of state (survivors,
+ * cursor, frame number) where the last executed frame put it. Asynchronous on the context's stream unless `sync` is set.
+ * Streaming contract: the staged-brick upload (kernel.cu:407-414) runs ONCE, before the first frame of the call -- the
+ * reference pairs one process_load_queue with one launch_kernels (main.cpp:142-143), so at most one staged batch exists
+ * per call; requests of all `frames` frames accumulate in the queue for the host to stage afterwards.
+ * After bm_set_counters with primary_ray_cnt > 0 the survivor records must be supplied with bm_import_rays first
+ * (BM_E_STATE otherwise); bm_launch_frame takes them from `queue` instead. */
 int bm_render(bm_context* ctx, float* blit_buffer_device, uint32_t frames, uint64_t target_paths, uint32_t flags, int sync);
 
 /* Hand the throughput path an explicit survivor set: `count` dense records (the layout bm_launch_frame leaves in queue2) become

@@ -93,6 +93,9 @@ class Oracle:
         L.orc_connect.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int]
         L.orc_frame.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint32, C.c_void_p, C.c_void_p, C.c_float, C.c_float,
                                 C.c_uint32, C.c_uint32, C.c_void_p, C.c_void_p, C.c_int]
+        L.orc_primary_rays_tiled.argtypes = [C.c_void_p, C.c_uint32, C.c_void_p, C.c_void_p, C.c_uint32, C.c_uint32, C.c_void_p]
+        L.orc_frame_tiled.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint32, C.c_void_p, C.c_void_p, C.c_float, C.c_float,
+                                      C.c_uint32, C.c_uint32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int]
         L.orc_sky_eval.argtypes = [C.c_size_t, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p]
         L.orc_cone_sample.argtypes = [C.c_void_p, C.c_float, C.c_void_p, C.c_void_p]
         L.orc_footprint_begin.argtypes = [C.c_void_p]
@@ -204,14 +207,17 @@ class OracleScene:
 class OracleRenderer:
     """Canonical (slot-index ordered) wavefront loop of the reference, on the CPU."""
 
-    def __init__(self, scene, width, height, n_slots, camera, sun=(0.05, 0.1)):
+    def __init__(self, scene, width, height, n_slots, camera, sun=(0.05, 0.1), tile=None):
+        """tile = (row0, rows, strip_rows, strip_count, strip_index): the multi-GPU image partition of bm_config (oracle.h);
+        None = the whole image, the reference's own mapping."""
         self.scene, self.L = scene, scene.L
         self.width, self.height, self.n_slots = width, height, n_slots
         self.camera, self.sun = camera, sun
+        self.tile = None if tile is None else np.array(tile, np.uint32)
         self.rays = np.zeros(n_slots, RAY_DTYPE)
         self.next = np.zeros(n_slots, RAY_DTYPE)
         self.shadows = np.zeros(n_slots, SHADOW_DTYPE)
-        self.accum = np.zeros((height, width, 4), np.float32)
+        self.accum = np.zeros((height if tile is None else int(tile[1]), width, 4), np.float32)
         self.state = FrameState(0, 0, 0, 1)
         self.stats = Stats()
 
@@ -226,10 +232,14 @@ class OracleRenderer:
         return r, u
 
     def primary_rays(self):
-        self.L.orc_primary_rays(self.rays.ctypes.data, self.n_slots, C.addressof(self.state), C.addressof(self.camera), self.width, self.height)
+        if self.tile is not None:
+            self.L.orc_primary_rays_tiled(self.rays.ctypes.data, self.n_slots, C.addressof(self.state), C.addressof(self.camera), self.width, self.height,
+                                          self.tile.ctypes.data)
+        else:
+            self.L.orc_primary_rays(self.rays.ctypes.data, self.n_slots, C.addressof(self.state), C.addressof(self.camera), self.width, self.height)
 
     def set_wavefront_globals(self):
-        self.L.orc_set_wavefront_globals(C.addressof(self.state), self.n_slots, self.width, self.height)
+        self.L.orc_set_wavefront_globals(C.addressof(self.state), self.n_slots, self.width, self.height if self.tile is None else int(self.tile[1]))
 
     def extend(self, threads=0):
         self.L.orc_extend(self.scene.h, self.rays.ctypes.data, self.n_slots, C.addressof(self.camera), C.addressof(self.stats), threads)
@@ -245,6 +255,12 @@ class OracleRenderer:
 
     def frame(self, threads=0):
         """kernel.cu:416-423 then main.cpp:146 (buffer swap)."""
+        if self.tile is not None:
+            self.L.orc_frame_tiled(self.scene.h, self.rays.ctypes.data, self.next.ctypes.data, self.shadows.ctypes.data, self.n_slots, C.addressof(self.state),
+                                   C.addressof(self.camera), self.sun[0], self.sun[1], self.width, self.height, self.tile.ctypes.data, self.accum.ctypes.data,
+                                   C.addressof(self.stats), threads)
+            self.rays, self.next = self.next, self.rays
+            return
         self.L.orc_frame(self.scene.h, self.rays.ctypes.data, self.next.ctypes.data, self.shadows.ctypes.data, self.n_slots, C.addressof(self.state),
                          C.addressof(self.camera), self.sun[0], self.sun[1], self.width, self.height, self.accum.ctypes.data,
                          C.addressof(self.stats), threads)

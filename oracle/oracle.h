@@ -119,6 +119,15 @@ void orc_connect(orc_scene*, const orc_shadow* shadows, const orc_frame_state* s
 void orc_frame(orc_scene*, orc_ray* rays, orc_ray* next, orc_shadow* shadows, uint32_t n_slots, orc_frame_state* state,
                const orc_camera*, float sun_x, float sun_y, uint32_t width, uint32_t height, float* accum, orc_stats* stats, int threads);
 
+/* Image partition of the multi-GPU mode (not in the reference; include/brickmap_b200.h bm_config.tile_* / strip_*).
+ * tile = {row0, rows, strip_rows, strip_count, strip_index}: the instance renders `rows` rows of the full image; kernel.cu:170-171
+ * runs inside the tile (pixel_index = row_in_tile * width + x), the camera mapping kernel.cu:183-184 uses the full-image row
+ * (row0 + r, or ((r / strip_rows) * strip_count + strip_index) * strip_rows + r % strip_rows). accum is rows * width * 4 floats. */
+void orc_primary_rays_tiled(orc_ray* rays, uint32_t n_slots, const orc_frame_state* state, const orc_camera*, uint32_t width, uint32_t height,
+                            const uint32_t tile[5]);
+void orc_frame_tiled(orc_scene*, orc_ray* rays, orc_ray* next, orc_shadow* shadows, uint32_t n_slots, orc_frame_state* state, const orc_camera*,
+                     float sun_x, float sun_y, uint32_t width, uint32_t height, const uint32_t tile[5], float* accum, orc_stats* stats, int threads);
+
 /* ---- sky (sunsky.cu) ----------------------------------------------------------------------------- */
 /* mode 0 = sun(), 1 = sky(), 2 = sunsky(); dirs/out are n*3 floats. */
 void orc_sky_eval(size_t n, const float* dirs, int mode, const float sun_dir[3], float* out);

@@ -35,6 +35,9 @@ VIEWS = {
     "256": dict(w=512, h=512, pos=(32.0, 32.0, 250.0), dir=unit([1, 1, -0.6])),
     "256lod": dict(w=512, h=512, pos=(-150.0, -120.0, 330.0), dir=unit([1, 0.9, -0.45])),  # outside the world: AABB entry + both LoD levels
     "4096": dict(w=1920, h=1080, pos=(512.0, 512.0, 300.0), dir=np.array([1, 0, 0], np.float32)),
+    # thin-lens camera (kernel.cu:85-103,191-198): lens radius > 0 pins ConcentricSampleDisk, the order in which the two lens draws are
+    # taken (unspecified in the source, kernel.cu:194) and the FMA placement of the lens path in the reference build
+    "256lens": dict(w=512, h=512, pos=(32.0, 32.0, 250.0), dir=unit([1, 1, -0.6]), lens=0.75, focal=12.5, lib="256"),
 }
 
 
@@ -69,7 +72,8 @@ def run_variant(variant, frames, stream_frames):
     v = VIEWS[variant]
     W, H = v["w"], v["h"]
     t0 = time.time()
-    ref = ob.Reference(variant, W, H)
+    lib_variant = v.get("lib", variant)
+    ref = ob.Reference(lib_variant, W, H)
     ref.generate()
     rng = np.random.default_rng(20261017)
     out = {"grid_size": ref.grid_size, "grid_height": ref.grid_height, "n_slots": ref.n_slots, "lod2": ref.lod2, "lod8": ref.lod8, "queue_size": ref.queue_size,
@@ -79,7 +83,8 @@ def run_variant(variant, frames, stream_frames):
     out["brick_counts"] = counts
     idx0, br0 = ref.host_supercell(0)
     out["sc0_indices"], out["sc0_bricks"] = idx0, br0[:64]
-    cam = ob.make_camera(position=v["pos"], direction=v["dir"])
+    cam = ob.make_camera(position=v["pos"], direction=v["dir"], focal=v.get("focal", 1.0), lens=v.get("lens", 0.0))
+    out["focal"], out["lens"] = np.float32(v.get("focal", 1.0)), np.float32(v.get("lens", 0.0))
     ref.set_camera(cam)
     ref.set_sun(0.05, 0.1)
     ref.upload_sun()
@@ -112,7 +117,7 @@ def run_variant(variant, frames, stream_frames):
         out["stream_accum_pix"], out["stream_accum_val"] = pix, acc.reshape(-1, 4)[pix]
         # fresh, empty device scene again for the resident part
         ref = None
-        ref = ob.Reference(variant, W, H)
+        ref = ob.Reference(lib_variant, W, H)
         ref.generate()
         ref.set_camera(cam)
         ref.set_sun(0.05, 0.1)
@@ -173,7 +178,7 @@ def run_variant(variant, frames, stream_frames):
 
 
 if __name__ == "__main__":
-    which = sys.argv[1:] or ["256", "256lod", "4096"]
+    which = sys.argv[1:] or ["256", "256lod", "4096", "256lens"]
     for variant in which:
         print("variant", variant)
         # one variant per process would be cleaner (the harness keeps global state); separate .so files keep them apart here

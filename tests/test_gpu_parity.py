@@ -28,7 +28,8 @@ def cfg_from_golden(g, **kw):
 
 def renderer_for(g, store, cfg=None):
     ren = bm.Renderer(cfg or store.cfg, store)
-    ren.set_camera(bm.make_camera(position=g["cam_pos"], direction=g["cam_dir"]))
+    ren.set_camera(bm.make_camera(position=g["cam_pos"], direction=g["cam_dir"], focal=float(g["focal"]) if "focal" in g else 1.0,
+                                  lens=float(g["lens"]) if "lens" in g else 0.0))
     ren.set_sun(float(g["sun"][0]), float(g["sun"][1]))
     return ren
 
@@ -134,11 +135,12 @@ def test_traversal_edge_cases_match_oracle(oracle, golden, stores):
 
 
 # ---- whole frames ----------------------------------------------------------------------------------------------------
-@pytest.mark.parametrize("variant,nonflat", [("256", False), ("256lod", True), ("4096", False)])
+@pytest.mark.parametrize("variant,nonflat", [("256", False), ("256lod", True), ("4096", False), ("256lens", False)])
 def test_launch_frame_matches_reference_golden(golden, stores, variant, nonflat):
-    """bm_launch_frame == launch_kernels: every buffer the reference leaves behind, frame after frame."""
+    """bm_launch_frame == launch_kernels: every buffer the reference leaves behind, frame after frame. 256lens: the reference
+    build's thin-lens camera (lens radius 0.75; kernel.cu:85-103,191-198)."""
     g = golden(variant)
-    store = stores(variant, nonflat=nonflat)
+    store = stores("256" if variant == "256lens" else variant, nonflat=nonflat)
     ren = renderer_for(g, store)
     state = bm.State(store.cfg)
     f = 1
@@ -393,59 +395,210 @@ def test_render_target_and_reset(golden, stores):
     assert float(blit[..., 3].sum()) == ren.stats()["terminations"] - st["terminations"]
 
 
-def test_tiles_compose_like_independent_renderers(oracle, golden):
-    """Multi-GPU partition: a context restricted to a row band equals the oracle run on that band's camera rays."""
+@pytest.mark.parametrize("slack", [1, 2])
+def test_render_target_slack_then_camera_move_matches_oracle(oracle, golden, stores, slack):
+    """bm_render asked for more frames than the path target needs: the frames the device skips must not move any state (which
+    survivor set is current, cursor, frame number). Odd and even slack, then a camera move (accumulation reset,
+    kernel.cu:387-403) and several more frames, everything against the oracle."""
     g = golden("256")
-    w, h = int(g["width"]), int(g["height"])
-    row0, rows = bm.tile_rows_for_rank(h, 1, 2)
-    cfg = cfg_from_golden(g, tile_row0=row0, tile_rows=rows)
-    store = bm.SceneStore(cfg, resident=True)
-    ren = renderer_for(g, store, cfg)
-    blit = torch.zeros(rows, w, 4, dtype=torch.float32, device="cuda")
-    ren.render(blit, 2)
+    ren = renderer_for(g, stores("256"))
+    _, oren = oracle_renderer(oracle, g)
+    h, w = int(g["height"]), int(g["width"])
+    target = 2 * h * w
+    executed = 0
+    while oren.stats.terminations < target:
+        oren.frame()
+        executed += 1
+    blit = torch.zeros(h, w, 4, dtype=torch.float32, device="cuda")
+    ren.render(blit, executed + slack, target_paths=target)
+    st = ren.stats()
+    assert st["frames"] == executed and st["terminations"] == oren.stats.terminations
+    c = ren.counters()
+    assert [c.primary_ray_cnt, c.start_position, c.frame] == [oren.state.primary_ray_cnt, oren.state.start_position, oren.state.frame]
+    assert_records_equal(ren.export_rays(), oren.rays[: c.primary_ray_cnt], what="survivors after a target stop with slack %d" % slack)
+    # continue WITHOUT a reset: the survivors must be picked up from the right set
+    ren.render(blit, 1)
+    oren.frame()
+    c = ren.counters()
+    assert_records_equal(ren.export_rays(), oren.rays[: c.primary_ray_cnt], what="survivors one frame after the stop")
+    # target stop again, then move the camera: reset, the next frames see none of the old survivors
+    ren.render(blit, 3 + slack, target_paths=1)  # target already met: runs no frame at all
+    assert ren.stats()["frames"] == executed + 1
+    pos = (float(g["cam_pos"][0]) + 11.0, float(g["cam_pos"][1]) + 5.0, float(g["cam_pos"][2]) - 3.0)
+    ren.set_camera(bm.make_camera(position=pos, direction=g["cam_dir"]))
+    oren.camera = ob.make_camera(position=pos, direction=g["cam_dir"])
+    oren.reset()
+    ren.render(blit, 3)
+    for _ in range(3):
+        oren.frame()
+    c = ren.counters()
+    assert [c.primary_ray_cnt, c.start_position, c.frame] == [oren.state.primary_ray_cnt, oren.state.start_position, oren.state.frame]
+    assert_records_equal(ren.export_rays(), oren.rays[: c.primary_ray_cnt], what="survivors after the camera move")
     acc = blit.cpu().numpy()
-    assert acc.shape == (rows, w, 4) and acc[..., 3].sum() == ren.stats()["terminations"]
-    # full-image run: the band's first-frame primaries see the same geometry -> same hit mask in the band
-    cfg_full = cfg_from_golden(g)
-    ren_full = renderer_for(g, bm.SceneStore(cfg_full, resident=True), cfg_full)
-    st_full = bm.State(cfg_full)
-    ren_full.launch_kernels(st_full)
-    st_band = bm.State(cfg)
-    ren_band = renderer_for(g, store, cfg)
-    ren_band.launch_kernels(st_band)
-    full, band = st_full.rays("work"), st_band.rays("work")
-    # slot i of the band renders pixel (i % w, row0 + i // w): same pixel as slot i + row0*w of the full image, other jitter seed
-    n = min(rows * w, len(band))
-    assert np.array_equal(band["pixel_index"][:n], np.arange(n, dtype=np.uint32))
-    assert np.array_equal(full["pixel_index"][row0 * w: row0 * w + 8], np.arange(row0 * w, row0 * w + 8, dtype=np.uint32))
-    agree = ((band["distance"][:n] < 1e20) == (full["distance"][row0 * w: row0 * w + n] < 1e20)).mean()
-    assert agree > 0.99, "band and full image disagree on hit/miss for %.2f%% of pixels" % (100 * (1 - agree))
+    assert np.array_equal(acc[..., 3], oren.accum[..., 3])
+    assert_close_rel(acc, oren.accum, RADIANCE_TOL, "accumulation after the camera move")
 
 
-def test_interleaved_strips_cover_the_image(golden, stores):
-    """bm_config.strip_*: two contexts owning alternating 8-row strips see, per pixel, the geometry of the full-image run."""
+def test_render_after_set_counters_needs_records(golden, stores):
+    """bm_set_counters with primary_ray_cnt > 0 hands the survivor set to the caller: bm_render refuses to guess (BM_E_STATE)
+    until bm_import_rays supplies the records; bm_launch_frame takes them from `queue`."""
     g = golden("256")
+    ren = renderer_for(g, stores("256"))
+    blit = torch.zeros(int(g["height"]), int(g["width"]), 4, dtype=torch.float32, device="cuda")
+    ren.set_counters(primary_ray_cnt=5, start_position=0, frame=1)
+    with pytest.raises(bm.BrickmapError):
+        ren.render(blit, 1)
+    ren.set_counters(primary_ray_cnt=0, start_position=0, frame=1)
+    ren.render(blit, 1)
+
+
+def test_multi_frame_render_uploads_once_while_streaming(oracle, golden):
+    """bm_render(frames > 1) on a streaming scene: the staged batch is uploaded before the FIRST frame only (one
+    process_load_queue per call, main.cpp:142-143); later frames append requests and must not re-apply stale staging entries
+    to new positions. Per call: render 2 frames, stage. The oracle does the same: upload, two frames, stage."""
+    g = golden("256")
+    cfg = cfg_from_golden(g)
+    store = bm.SceneStore(cfg, resident=False)
+    ren = renderer_for(g, store, cfg)
+    s, oren = oracle_renderer(oracle, g, resident=False)
+    blit = torch.zeros(int(g["height"]), int(g["width"]), 4, dtype=torch.float32, device="cuda")
+    for call in range(4):
+        ren.render(blit, 2)
+        cnt, pos = ren.load_queue()
+        store.process_load_queue(ren.stream)
+        if call:
+            s.stream()
+        oren.frame(threads=1)
+        oren.frame(threads=1)
+        ocnt, opos = s.queue()
+        assert cnt == ocnt, "call %d: %d requests vs oracle %d" % (call, cnt, ocnt)
+        if cnt <= int(g["queue_size"]):
+            assert sorted(map(tuple, pos)) == sorted(map(tuple, opos))
+    ren.synchronize()
+    for sc in range(store.superchunks):
+        mine, want = store.indices(sc), s.gpu_indices(sc)
+        assert np.array_equal(mine & ~np.uint32(0xFFF), want & ~np.uint32(0xFFF)), "index words (slot bits masked) differ in superchunk %d" % sc
+        loaded = np.flatnonzero(mine & 0x80000000)
+        assert (mine[loaded] & 0xFFF).max(initial=0) < max(store.brick_count(sc), 1), "slot outside the superchunk's brick array"
+    assert_close_rel(blit.cpu().numpy(), oren.accum, RADIANCE_TOL, "accumulation, two frames per streaming call")
+
+
+def test_exact_paths_mode_matches_oracle(oracle, golden, stores):
+    """BM_FRAME_EXACT_PATHS: exactly target_paths paths are started since the reset -- the last frames take only the fresh
+    primaries that are still missing, then only survivors. Every pixel ends with exactly spp finished paths, and every frame is
+    the reference algorithm run with that frame's slot count (the oracle is driven with the same counts)."""
+    g = golden("256")
+    ren = renderer_for(g, stores("256"))
+    _, oren = oracle_renderer(oracle, g)
+    h, w, n = int(g["height"]), int(g["width"]), int(g["n_slots"])
+    spp = 3
+    target = spp * h * w
+    frames = 0
+    while oren.stats.terminations < target:
+        c = oren.state.primary_ray_cnt
+        started = oren.stats.terminations + c
+        oren.n_slots = c + min(n - c, target - started)
+        assert oren.n_slots > 0
+        oren.frame()
+        frames += 1
+    assert oren.stats.terminations == target and oren.state.primary_ray_cnt == 0
+    blit = torch.zeros(h, w, 4, dtype=torch.float32, device="cuda")
+    ren.render(blit, frames + 5, target_paths=target, flags=R.FRAME_EXACT_PATHS)
+    st = ren.stats()
+    assert st["frames"] == frames and st["terminations"] == target
+    assert st["extend_rays"] + st["shadow_rays"] == oren.stats.rays
+    c = ren.counters()
+    assert [c.primary_ray_cnt, c.start_position, c.frame] == [0, oren.state.start_position, oren.state.frame]
+    acc = blit.cpu().numpy()
+    assert np.all(acc[..., 3] == float(spp)), "every pixel has exactly spp finished paths"
+    assert_close_rel(acc, oren.accum, RADIANCE_TOL, "accumulation in exact-paths mode")
+    # a sun move resets; the mode then runs the same number of paths again, continuing cursor and frame number
+    ren.set_sun(0.3, 0.2)
+    ren.render(blit, 100, target_paths=target, flags=R.FRAME_EXACT_PATHS)
+    assert ren.stats()["terminations"] == 2 * target and float(blit[..., 3].min()) == float(blit[..., 3].max()) == float(spp)
+
+
+def test_extend_only_matches_reference_golden(golden, stores):
+    """BM_FRAME_EXTEND_ONLY (BASELINE config 2: primary rays only): primary_rays + extend of the reference, nothing shaded."""
+    g = golden("4096")
+    store = stores("4096")
+    ren = renderer_for(g, store)
+    state = bm.State(store.cfg)
+    ren.launch_kernels(state, flags=R.FRAME_EXTEND_ONLY)
+    ext = state.rays("work")
+    assert int((ext["distance"] < 1e20).sum()) == int(g["f1_ext_hits"])
+    assert_records_equal(ext[g["f1_ext_idx"]], g["f1_ext"], what="post-extend records, extend-only frame")
+    c = ren.counters()
+    assert [c.primary_ray_cnt, c.shadow_ray_cnt, c.start_position, c.frame] == [0, 0, int(g["f1_counters"][2]), 2]
+    assert float(state.blit_buffer.abs().sum()) == 0.0
+
+
+def _check_tile_against_oracle(oracle, g, store_for, tile_kw, tile, frames=3):
+    """One context restricted to an image partition == the oracle run with the same row mapping: post-extend records and
+    survivors bit for bit every frame (bm_launch_frame), alpha exactly and radiance to 1e-4 (both entry points)."""
     w, h = int(g["width"]), int(g["height"])
-    cfg_full = cfg_from_golden(g)
-    ren_full = renderer_for(g, stores("256"), cfg_full)
-    st_full = bm.State(cfg_full)
-    ren_full.launch_kernels(st_full)
-    full_hit = (st_full.rays("work")["distance"] < 1e20)[: w * h].reshape(h, w)
-    seen = np.zeros(h, bool)
-    for rank in range(2):
-        rows, image_rows = bm.strip_rows_for_rank(h, rank, 2, 8)
-        cfg = cfg_from_golden(g, tile_rows=rows, strip_rows=8, strip_count=2, strip_index=rank)
-        ren = renderer_for(g, stores("256"), cfg)
-        st = bm.State(cfg)
-        ren.launch_kernels(st)
-        rays = st.rays("work")[: rows * w]
-        assert np.array_equal(rays["pixel_index"], np.arange(rows * w, dtype=np.uint32)), "pixel index is local to the rank's buffer"
-        hit = (rays["distance"] < 1e20).reshape(rows, w)
-        agree = (hit == full_hit[image_rows]).mean()
-        assert agree > 0.99, "rank %d disagrees with the full image on %.2f%% of its pixels" % (rank, 100 * (1 - agree))
-        assert st.blit_buffer.shape == (rows, w, 4)
-        seen[image_rows] = True
-    assert seen.all()
+    cfg = cfg_from_golden(g, **tile_kw)
+    store = store_for(cfg)
+    ren = renderer_for(g, store, cfg)
+    fused = renderer_for(g, store, cfg)
+    s = ob.OracleScene(oracle, int(g["grid_size"]), int(g["grid_height"]), int(g["lod2"]), int(g["lod8"]), int(g["queue_size"])).generate_terrain().set_residency(True)
+    oren = ob.OracleRenderer(s, w, h, int(g["n_slots"]), ob.make_camera(position=g["cam_pos"], direction=g["cam_dir"]), tuple(float(v) for v in g["sun"]), tile=tile)
+    state = bm.State(cfg)
+    rows = tile[1]
+    assert state.blit_buffer.shape == (rows, w, 4)
+    for f in range(frames):
+        ren.launch_kernels(state)
+        oren.primary_rays()
+        oren.set_wavefront_globals()
+        oren.extend()
+        ext = oren.rays.copy()
+        oren.shade()
+        oren.connect()
+        oren.state.frame += 1
+        oren.rays, oren.next = oren.next, oren.rays
+        c = ren.counters()
+        assert [c.primary_ray_cnt, c.shadow_ray_cnt, c.start_position] == [oren.state.primary_ray_cnt, oren.state.shadow_ray_cnt, oren.state.start_position]
+        assert_records_equal(state.rays("work"), ext, what="tile %s frame %d post-extend" % (tile, f + 1))
+        assert_records_equal(state.rays("next", c.primary_ray_cnt), oren.rays[: c.primary_ray_cnt], what="tile %s frame %d survivors" % (tile, f + 1))
+        state.swap()
+    acc = state.blit_buffer.cpu().numpy()
+    assert np.array_equal(acc[..., 3], oren.accum[..., 3]), "alpha per pixel of the tile"
+    assert_close_rel(acc, oren.accum, RADIANCE_TOL, "tile %s accumulation" % (tile,))
+    blit = torch.zeros(rows, w, 4, dtype=torch.float32, device="cuda")
+    fused.render(blit, frames)
+    acc = blit.cpu().numpy()
+    assert np.array_equal(acc[..., 3], oren.accum[..., 3])
+    assert_close_rel(acc, oren.accum, RADIANCE_TOL, "tile %s accumulation, fused path" % (tile,))
+    assert_records_equal(fused.export_rays(), oren.rays[: oren.state.primary_ray_cnt], what="tile %s survivors, fused path" % (tile,))
+    return acc
+
+
+@pytest.mark.parametrize("world,rank", [(2, 0), (2, 1), (8, 0), (8, 3), (8, 7)])
+def test_interleaved_strips_match_oracle_with_the_same_tiling(oracle, golden, stores, world, rank):
+    """a rank's context (strips of 8 rows dealt round-robin, the partition bench.py uses) equals the CPU oracle run
+    with the same tiling -- bit for bit on rays, exactly on alpha, 1e-4 on radiance."""
+    g = golden("256")
+    h = int(g["height"])
+    rows, image_rows = bm.strip_rows_for_rank(h, rank, world, 8)
+    tile = (0, rows, 8, world, rank)
+    acc = _check_tile_against_oracle(oracle, g, lambda cfg: stores("256"), dict(tile_rows=rows, strip_rows=8, strip_count=world, strip_index=rank), tile)
+    assert acc.shape[0] == len(image_rows)
+
+
+@pytest.mark.parametrize("world,rank", [(2, 1), (3, 0)])
+def test_row_bands_match_oracle_with_the_same_tiling(oracle, golden, stores, world, rank):
+    """The contiguous-band partition (bm_config.tile_row0 / tile_rows), including a band height that does not divide the image."""
+    g = golden("256")
+    row0, rows = bm.tile_rows_for_rank(int(g["height"]), rank, world)
+    _check_tile_against_oracle(oracle, g, lambda cfg: stores("256"), dict(tile_row0=row0, tile_rows=rows), (row0, rows, 0, 1, 0))
+
+
+def test_strips_on_an_outside_view_with_lod_match_oracle(oracle, golden, stores):
+    """Strips on the outside-the-world view (AABB entry, both LoD levels), ragged last strip (rows not a multiple of 8 * world)."""
+    g = golden("256lod")
+    h = int(g["height"])
+    rows, _ = bm.strip_rows_for_rank(h, 2, 5, 8)
+    _check_tile_against_oracle(oracle, g, lambda cfg: stores("256lod"), dict(tile_rows=rows, strip_rows=8, strip_count=5, strip_index=2), (0, rows, 8, 5, 2), frames=2)
 
 
 # ---- streaming ----------------------------------------------------------------------------------------------------

@@ -25,7 +25,7 @@ def make_scene(oracle, g):
 
 
 def make_renderer(scene, g):
-    cam = ob.make_camera(position=g["cam_pos"], direction=g["cam_dir"])
+    cam = ob.make_camera(position=g["cam_pos"], direction=g["cam_dir"], focal=float(g["focal"]) if "focal" in g else 1.0, lens=float(g["lens"]) if "lens" in g else 0.0)
     return ob.OracleRenderer(scene, int(g["width"]), int(g["height"]), int(g["n_slots"]), cam, tuple(float(v) for v in g["sun"]))
 
 
@@ -78,9 +78,13 @@ def test_traversal_matches_reference(oracle, golden, scenes, variant):
     assert 0 < hit.sum() < n
 
 
-@pytest.mark.parametrize("variant", ["256", "256lod", "4096"])
+@pytest.mark.parametrize("variant", ["256", "256lod", "4096", "256lens"])
 def test_canonical_frames_match_reference(oracle, golden, scenes, variant):
+    """256lens: thin-lens camera (lens radius 0.75, focal distance 12.5): pins ConcentricSampleDisk (kernel.cu:85-103), the order of
+    the two lens draws (unspecified in the source, kernel.cu:194) and the FMA placement of kernel.cu:191-198 in the reference build."""
     g, s = golden(variant), scenes(variant)
+    if variant == "256lens":
+        assert float(g["lens"]) > 0
     s.set_residency(True)
     ren = make_renderer(s, g)
     f = 1
@@ -125,3 +129,39 @@ def test_streaming_matches_reference(oracle, golden):
         f += 1
     assert f == 4
     assert_close_rel(ren.accum.reshape(-1, 4)[g["stream_accum_pix"]], g["stream_accum_val"], RADIANCE_TOL, "accumulation after streaming frames")
+
+
+def test_tiled_oracle_is_the_reference_mapping_inside_the_tile(oracle, golden, scenes):
+    """The multi-GPU image partition of the oracle (oracle.h, Tile): the whole-image tile is the reference's own mapping bit for
+    bit; a strip tile visits its own pixels in raster order (kernel.cu:170-171 inside the tile) and points each ray through
+    the full-image row its buffer row stands for (kernel.cu:183-184)."""
+    g, s = golden("256"), scenes("256")
+    s.set_residency(True)
+    w, h, n = 96, 64, 96 * 64
+    cam = ob.make_camera(position=g["cam_pos"], direction=g["cam_dir"])
+    full = ob.OracleRenderer(s, w, h, n, cam)
+    full.primary_rays()
+    whole = ob.OracleRenderer(s, w, h, n, cam, tile=(0, h, 0, 1, 0))
+    whole.primary_rays()
+    assert full.rays.tobytes() == whole.rays.tobytes()
+    right, up = full.camera_basis()
+    d0 = np.asarray(g["cam_dir"], np.float64)
+    for tile, image_rows in (((0, 32, 8, 2, 1), [r for r in range(h) if (r // 8) % 2 == 1]), ((16, 24, 0, 1, 0), list(range(16, 40)))):
+        t = ob.OracleRenderer(s, w, h, tile[1] * w, cam, tile=tile)
+        t.primary_rays()
+        assert np.array_equal(t.rays["pixel_index"], np.arange(tile[1] * w, dtype=np.uint32))
+        # the ray of buffer pixel (x, r) goes through image pixel (x, image_rows[r]) up to the sub-pixel jitter
+        x = (np.arange(tile[1] * w) % w).astype(np.float64)
+        y = np.repeat(np.array(image_rows, np.float64), w)
+        lo = d0 + ((x - 1) / w - 0.5)[:, None] * right + ((h - y) / h - 0.5)[:, None] * up
+        hi = d0 + ((x + 0) / w - 0.5)[:, None] * right + ((h - (y - 1)) / h - 0.5)[:, None] * up
+        mid = 0.5 * (lo + hi)
+        mid /= np.linalg.norm(mid, axis=1, keepdims=True)
+        cosang = (mid * t.rays["direction"].astype(np.float64)).sum(1)
+        assert cosang.min() > np.cos(2.5 / h), "tile %s: a ray leaves its pixel (min cos %.6f)" % (tile, cosang.min())
+        assert t.accum.shape == (tile[1], w, 4)
+    # two strip instances together finish the same number of paths as their pixels ask for
+    t = ob.OracleRenderer(s, w, h, 32 * w, cam, tile=(0, 32, 8, 2, 0))
+    for _ in range(3):
+        t.frame()
+    assert t.accum[..., 3].sum() == t.stats.terminations > 0
