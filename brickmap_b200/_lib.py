@@ -52,6 +52,7 @@ SIGNATURES = {
     "bm_reset_stats": (C.c_int, [_P]),
     "bm_launch_frame": (C.c_int, [_P, _P, _P, _P, _P, C.c_uint32]),
     "bm_render": (C.c_int, [_P, _P, C.c_uint32, C.c_uint64, C.c_uint32, C.c_int]),
+    "bm_extend_primaries": (C.c_int, [_P, _P, C.c_uint32, C.c_int]),
     "bm_import_rays": (C.c_int, [_P, _P, C.c_uint32]),
     "bm_export_rays": (C.c_int, [_P, _P]),
     "bm_render_to_host": (C.c_int, [_P, _P, C.c_uint32, C.c_uint64, C.c_uint32, _P, _P, _P]),

@@ -36,6 +36,19 @@ def build(force=False, verbose=False):
     return LIB
 
 
+def build_variant(name, defines, verbose=False):
+    """A/B builds for measurements (tools/gpu_ab.sh, BRICKMAP_B200_LIB): libbrickmap_b200_<name>.so with extra -D switches."""
+    out = os.path.join(HERE, "libbrickmap_b200_%s.so" % name)
+    nvcc = os.environ.get("NVCC", "nvcc")
+    cmd = [nvcc] + NVCC_FLAGS + ["-D" + d for d in defines] + (["-Xptxas", "-v"] if verbose else []) + ["-o", out] + [os.path.join(CSRC, s) for s in SOURCES]
+    subprocess.check_call(cmd)
+    return out
+
+
 if __name__ == "__main__":
-    build(force="--force" in sys.argv, verbose="-v" in sys.argv)
-    print(LIB)
+    if "--variant" in sys.argv:  # python -m brickmap_b200.build --variant bulk BM_BULK_PROLOGUE=1 ...
+        i = sys.argv.index("--variant")
+        print(build_variant(sys.argv[i + 1], [a for a in sys.argv[i + 2:] if not a.startswith("-")], verbose="-v" in sys.argv))
+    else:
+        build(force="--force" in sys.argv, verbose="-v" in sys.argv)
+        print(LIB)

@@ -492,6 +492,25 @@ __device__ __forceinline__ bool intersect_voxel(const SceneView& sv, const uint3
 }
 
 // ---- sun-sky model (sunsky.cu) -------------------------------------------------------------------------------
+// Radiance only has to agree with the reference to 1e-4 relative (north star) and feeds nothing geometric, so the transcendental
+// and division steps of the sky model may use the hardware approximations (ex2.approx / rcp.approx / rsqrt.approx, <= 2 ulp each,
+// ~1e-6 relative on the result): BM_FAST_RADIANCE=1. Everything that decides a ray's geometry stays IEEE-exact.
+#ifndef BM_FAST_RADIANCE
+#define BM_FAST_RADIANCE 0
+#endif
+#if BM_FAST_RADIANCE
+__device__ __forceinline__ float r_exp(float x) { return __expf(x); }
+__device__ __forceinline__ float r_div(float a, float b) { return __fdividef(a, b); }
+__device__ __forceinline__ float r_sqrt(float x) {
+	float r;
+	asm("sqrt.approx.f32 %0, %1;" : "=f"(r) : "f"(x));
+	return r;
+}
+#else
+__device__ __forceinline__ float r_exp(float x) { return expf(x); }
+__device__ __forceinline__ float r_div(float a, float b) { return a / b; }
+__device__ __forceinline__ float r_sqrt(float x) { return sqrtf(x); }
+#endif
 struct SkyTerms {
 	F3 fex, sky;
 	float cos_view_sun;
@@ -501,18 +520,18 @@ __device__ __forceinline__ SkyTerms sky_terms(const FrameParams& fp, const F3& v
 	r.cos_view_sun = view.x * fp.sun_dir.x + view.y * fp.sun_dir.y + view.z * fp.sun_dir.z;
 	const float cos_up_view = view.z;  // dot(up, viewDir), up = (0,0,1) (sunsky.cu:5)
 	const float zenith = gmax(0.0f, cos_up_view);
-	const float rl = 8.4E3f / zenith;   // rayleighZenithLength (sunsky.cuh:37)
-	const float ml = 1.25E3f / zenith;  // mieZenithLength (sunsky.cuh:38)
-	r.fex = F3{ expf(-(fp.rayleigh.x * rl + fp.mie.x * ml)), expf(-(fp.rayleigh.y * rl + fp.mie.y * ml)), expf(-(fp.rayleigh.z * rl + fp.mie.z * ml)) };
+	const float rl = r_div(8.4E3f, zenith);   // rayleighZenithLength (sunsky.cuh:37)
+	const float ml = r_div(1.25E3f, zenith);  // mieZenithLength (sunsky.cuh:38)
+	r.fex = F3{ r_exp(-(fp.rayleigh.x * rl + fp.mie.x * ml)), r_exp(-(fp.rayleigh.y * rl + fp.mie.y * ml)), r_exp(-(fp.rayleigh.z * rl + fp.mie.z * ml)) };
 	const float c = r.cos_view_sun;
 	const float rp = fp.rayleigh_k * (1.0f + c * c);                                    // RayleighPhase, sunsky.cu:10-12
 	const float hx = 1.0f - 2.0f * fp.hg_g * c + fp.hg_g * fp.hg_g;
-	const float hg = fp.hg_k / (hx * sqrtf(hx));                                        // hgPhase, sunsky.cu:20-22 (x^1.5 = x sqrt x)
+	const float hg = r_div(fp.hg_k, hx * r_sqrt(hx));                                        // hgPhase, sunsky.cu:20-22 (x^1.5 = x sqrt x)
 	const F3 light{ fp.rayleigh.x * rp + fp.mie.x * hg, fp.rayleigh.y * rp + fp.mie.y * hg, fp.rayleigh.z * rp + fp.mie.z * hg };
-	const F3 se{ fp.sun_e * (light.x / fp.total.x), fp.sun_e * (light.y / fp.total.y), fp.sun_e * (light.z / fp.total.z) };
+	const F3 se{ fp.sun_e * r_div(light.x, fp.total.x), fp.sun_e * r_div(light.y, fp.total.y), fp.sun_e * r_div(light.z, fp.total.z) };
 	const float a = fp.mix_a;
-	r.sky = F3{ (se.x * (1.0f - r.fex.x)) * (1.0f * (1.0f - a) + sqrtf(se.x * r.fex.x) * a), (se.y * (1.0f - r.fex.y)) * (1.0f * (1.0f - a) + sqrtf(se.y * r.fex.y) * a),
-		        (se.z * (1.0f - r.fex.z)) * (1.0f * (1.0f - a) + sqrtf(se.z * r.fex.z) * a) };
+	r.sky = F3{ (se.x * (1.0f - r.fex.x)) * (1.0f * (1.0f - a) + r_sqrt(se.x * r.fex.x) * a), (se.y * (1.0f - r.fex.y)) * (1.0f * (1.0f - a) + r_sqrt(se.y * r.fex.y) * a),
+		        (se.z * (1.0f - r.fex.z)) * (1.0f * (1.0f - a) + r_sqrt(se.z * r.fex.z) * a) };
 	return r;
 }
 // sun(), sunsky.cu:32-74: only the extinction term depends on the view direction; the "disk" factor is 1 unless
@@ -520,11 +539,11 @@ __device__ __forceinline__ SkyTerms sky_terms(const FrameParams& fp, const F3& v
 __device__ __forceinline__ F3 sun_radiance(const FrameParams& fp, const F3& view) {
 	const float cvs = view.x * fp.sun_dir.x + view.y * fp.sun_dir.y + view.z * fp.sun_dir.z;
 	const float zenith = gmax(0.0f, view.z);
-	const float rl = 8.4E3f / zenith, ml = 1.25E3f / zenith;
+	const float rl = r_div(8.4E3f, zenith), ml = r_div(1.25E3f, zenith);
 	const float disk = (fp.sun_angular_cos < (cvs != 0.0f ? 1.0f : 0.0f)) ? 1.0f : 0.0f;
 	const float k = fp.sun_e * 19000.0f;
-	return F3{ 0.01f * ((k * expf(-(fp.rayleigh.x * rl + fp.mie.x * ml))) * disk), 0.01f * ((k * expf(-(fp.rayleigh.y * rl + fp.mie.y * ml))) * disk),
-		       0.01f * ((k * expf(-(fp.rayleigh.z * rl + fp.mie.z * ml))) * disk) };
+	return F3{ 0.01f * ((k * r_exp(-(fp.rayleigh.x * rl + fp.mie.x * ml))) * disk), 0.01f * ((k * r_exp(-(fp.rayleigh.y * rl + fp.mie.y * ml))) * disk),
+		       0.01f * ((k * r_exp(-(fp.rayleigh.z * rl + fp.mie.z * ml))) * disk) };
 }
 __device__ __forceinline__ F3 sky_radiance(const FrameParams& fp, const F3& view) {  // sky(), sunsky.cu:76-114 (SkyFactor = 1)
 	const SkyTerms t = sky_terms(fp, view);
@@ -533,7 +552,7 @@ __device__ __forceinline__ F3 sky_radiance(const FrameParams& fp, const F3& view
 __device__ __forceinline__ F3 sunsky_radiance(const FrameParams& fp, const F3& view) {  // sunsky(), sunsky.cu:116-161
 	if (fp.sun_angular_cos == 1.0f) return F3{ 1.0f, 0.0f, 0.0f };
 	const SkyTerms t = sky_terms(fp, view);
-	float s = (t.cos_view_sun - fp.sun_angular_cos) / ((fp.sun_angular_cos + 0.00002f) - fp.sun_angular_cos);  // glm::smoothstep
+	float s = r_div(t.cos_view_sun - fp.sun_angular_cos, (fp.sun_angular_cos + 0.00002f) - fp.sun_angular_cos);  // glm::smoothstep
 	s = gmin(gmax(s, 0.0f), 1.0f);
 	const float disk = s * s * (3.0f - 2.0f * s);
 	const float k = fp.sun_e * 19000.0f;

@@ -54,6 +54,37 @@ struct QSched {
 	int resume_at;     // queued rays are resumed as soon as this many have piled up (<= 32)
 };
 
+// The block's copy of the emptiness bitmap (46 KiB at reference dims). BM_BULK_PROLOGUE=1: ONE bulk asynchronous copy global -> shared
+// (cp.async.bulk, the 1-D form of TMA; SASS UBLKCP) issued by thread 0 and awaited by all threads on an mbarrier, instead of the
+// cooperative __ldg / st.shared loop. `words` is a multiple of 4 (16-byte granularity of the bulk copy), both addresses are 16-byte aligned.
+__device__ __forceinline__ void stage_bitmap(uint32_t* s_coarse, const uint32_t* g_coarse, uint32_t words) {
+#if BM_BULK_PROLOGUE
+	__shared__ __align__(8) unsigned long long s_bar;
+	const uint32_t bar = (uint32_t)__cvta_generic_to_shared(&s_bar), dst = (uint32_t)__cvta_generic_to_shared(s_coarse), bytes = words * 4u;
+	if (threadIdx.x == 0) {
+		asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(bar));
+		asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+	}
+	__syncthreads();
+	if (threadIdx.x == 0) {
+		asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+		asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst), "l"(g_coarse), "r"(bytes), "r"(bar) : "memory");
+	}
+	asm volatile(
+	    "{\n\t"
+	    ".reg .pred p;\n\t"
+	    "BM_WAIT_BITMAP:\n\t"
+	    "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], 0;\n\t"
+	    "@p bra BM_WAIT_DONE;\n\t"
+	    "bra BM_WAIT_BITMAP;\n\t"
+	    "BM_WAIT_DONE:\n\t"
+	    "}" ::"r"(bar) : "memory");
+#else
+	for (uint32_t i = threadIdx.x; i < words; i += blockDim.x) s_coarse[i] = __ldg(g_coarse + i);
+	__syncthreads();
+#endif
+}
+
 // RECORD (bm_launch_frame): additionally leaves the post-extend record of every slot and the shadow-ray records, like frame_kernel<RECORD>
 template <bool STOCK, bool RECORD>
 __global__ void __launch_bounds__(kQBlock, 1) frame_kernel_q(const FrameParams fp, const SceneView sv, const FrameIO io, const QSched sch) {
@@ -61,9 +92,8 @@ __global__ void __launch_bounds__(kQBlock, 1) frame_kernel_q(const FrameParams f
 	extern __shared__ uint32_t s_coarse[];
 	DeviceState* st = io.st;
 	if (st->done) return;
-	for (uint32_t i = threadIdx.x; i < sv.coarse_words; i += blockDim.x) s_coarse[i] = __ldg(sv.coarse + i);
+	stage_bitmap(s_coarse, sv.coarse, sv.coarse_words);
 	const uint32_t* coarse = s_coarse;
-	__syncthreads();
 
 	const uint32_t c = st->primary_ray_cnt;
 	const uint32_t start = st->start_position;

@@ -31,6 +31,9 @@
 #include <new>
 #include <vector>
 
+#include <cub/device/device_radix_sort.cuh>
+#include <cub/device/device_scan.cuh>
+
 #include "bm_device.cuh"
 
 namespace bm {
@@ -398,77 +401,49 @@ __global__ void upload_kernel(const SceneView sv, const bm_brick* bricks_queue, 
 	sv.indices[sc][local] = word;
 }
 
-// Merge of the all-gathered request blocks (see include/brickmap_b200.h). One block of 1024 threads.
-// gathered: world blocks of (1 + 3q) int32 = {count, positions}. Entry order: rank-major, queue order inside.
-__global__ void __launch_bounds__(1024) requests_merge_kernel(const SceneView sv, const int32_t* gathered, int world) {
-	extern __shared__ int32_t s_mem[];
+// Merge of the all-gathered request blocks (see include/brickmap_b200.h), for any world size and queue size.
+// gathered: world blocks of (1 + 3q) int32 = {count, positions}. Entry order: rank-major, queue order inside; flat index i = r q + k.
+// First occurrences are found with a STABLE sort by cell number (cub radix sort): the head of every run of equal keys is the
+// earliest entry of that cell. An exclusive scan of the head flags in flat order gives each surviving entry its place.
+__global__ void merge_keys_kernel(const SceneView sv, const int32_t* gathered, int world, uint32_t* keys, uint32_t* vals) {
 	const uint32_t q = sv.queue_size;
-	const uint32_t stride = 1 + 3 * q;
-	int32_t* s_key_x = s_mem;                      // world * q
-	int32_t* s_key_y = s_key_x + (size_t)world * q;
-	int32_t* s_key_z = s_key_y + (size_t)world * q;
-	int32_t* s_flag = s_key_z + (size_t)world * q;  // 1 = first occurrence
-	__shared__ uint32_t s_total;
-	__shared__ uint32_t s_base[32];
-	// flatten
-	uint32_t n = 0;
-	for (int r = 0; r < world; r++) n += min((uint32_t)gathered[(size_t)r * stride], q);
-	for (uint32_t i = threadIdx.x; i < n; i += blockDim.x) {
-		uint32_t k = i;
-		int r = 0;
-		for (; r < world; r++) {
-			const uint32_t c = min((uint32_t)gathered[(size_t)r * stride], q);
-			if (k < c) break;
-			k -= c;
-		}
-		const int32_t* p = gathered + (size_t)r * stride + 1 + 3 * k;
-		s_key_x[i] = p[0]; s_key_y[i] = p[1]; s_key_z[i] = p[2];
+	const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+	if (i >= (uint32_t)world * q) return;
+	const uint32_t r = i / q, k = i % q;
+	const int32_t* block = gathered + (size_t)r * (1 + 3 * (size_t)q);
+	uint32_t key = 0xFFFFFFFFu;  // entries past a block's count sort to the end
+	if (k < min((uint32_t)block[0], q)) {
+		const int32_t* p = block + 1 + 3 * k;
+		key = (uint32_t)p[0] + (uint32_t)sv.cells * ((uint32_t)p[1] + (uint32_t)sv.cells * (uint32_t)p[2]);
 	}
-	__syncthreads();
-	for (uint32_t i = threadIdx.x; i < n; i += blockDim.x) {
-		int first = 1;
-		const int32_t x = s_key_x[i], y = s_key_y[i], z = s_key_z[i];
-		for (uint32_t j = 0; j < i; j++)
-			if (s_key_x[j] == x && s_key_y[j] == y && s_key_z[j] == z) { first = 0; break; }
-		s_flag[i] = first;
+	keys[i] = key;
+	vals[i] = i;
+}
+__global__ void merge_heads_kernel(const uint32_t* sorted_keys, const uint32_t* sorted_vals, uint32_t n, uint32_t* first) {
+	const uint32_t p = blockIdx.x * blockDim.x + threadIdx.x;
+	if (p >= n) return;
+	const uint32_t key = sorted_keys[p];
+	first[sorted_vals[p]] = (key != 0xFFFFFFFFu && (p == 0 || sorted_keys[p - 1] != key)) ? 1u : 0u;
+}
+__global__ void merge_write_kernel(const SceneView sv, const int32_t* gathered, int world, const uint32_t* first, const uint32_t* place) {
+	const uint32_t q = sv.queue_size;
+	const uint32_t n = (uint32_t)world * q;
+	const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+	if (i >= n) return;
+	if (i == n - 1) *sv.load_queue_count = place[i] + first[i];  // all unique requests; may exceed q, consumers clamp (kernel.cu:409)
+	if (!first[i]) return;
+	const int32_t* p = gathered + (size_t)(i / q) * (1 + 3 * (size_t)q) + 1 + 3 * (i % q);
+	const int px = p[0], py = p[1], pz = p[2];
+	const int sc = (px >> 4) + (py >> 4) * sv.supergrid_xy + (pz >> 4) * sv.supergrid_xy * sv.supergrid_xy;
+	const int local = (px & 15) + (py & 15) * 16 + (pz & 15) * 256;
+	uint32_t* word = sv.indices[sc] + local;
+	const uint32_t out = place[i];
+	if (out < q) {
+		sv.load_queue[3 * out] = px; sv.load_queue[3 * out + 1] = py; sv.load_queue[3 * out + 2] = pz;
+		atomicOr(word, BM_BRICK_REQUESTED_BIT);
+	} else {
+		atomicAnd(word, ~BM_BRICK_REQUESTED_BIT);  // did not make the cut: released for a later frame (voxel.cuh:237-240)
 	}
-	__syncthreads();
-	// ordered compaction: thread t handles the contiguous chunk [t*per, (t+1)*per)
-	const uint32_t per = (n + blockDim.x - 1) / blockDim.x;
-	const uint32_t b = min(n, threadIdx.x * per), e = min(n, b + per);
-	uint32_t mine = 0;
-	for (uint32_t i = b; i < e; i++) mine += s_flag[i];
-	uint32_t incl = mine;
-	const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-	for (int o = 1; o < 32; o <<= 1) {
-		const uint32_t v = __shfl_up_sync(0xFFFFFFFFu, incl, o);
-		if (lane >= (uint32_t)o) incl += v;
-	}
-	if (lane == 31) s_base[warp] = incl;
-	__syncthreads();
-	if (threadIdx.x == 0) {
-		uint32_t run = 0;
-		for (int w = 0; w < 32; w++) { const uint32_t v = s_base[w]; s_base[w] = run; run += v; }
-		s_total = run;
-	}
-	__syncthreads();
-	uint32_t out = s_base[warp] + incl - mine;
-	for (uint32_t i = b; i < e; i++) {
-		if (!s_flag[i]) continue;
-		const int px = s_key_x[i], py = s_key_y[i], pz = s_key_z[i];
-		const int sc = (px >> 4) + (py >> 4) * sv.supergrid_xy + (pz >> 4) * sv.supergrid_xy * sv.supergrid_xy;
-		const int local = (px & 15) + (py & 15) * 16 + (pz & 15) * 256;
-		uint32_t* word = sv.indices[sc] + local;
-		if (out < q) {
-			sv.load_queue[3 * out] = px; sv.load_queue[3 * out + 1] = py; sv.load_queue[3 * out + 2] = pz;
-			atomicOr(word, BM_BRICK_REQUESTED_BIT);
-		} else {
-			atomicAnd(word, ~BM_BRICK_REQUESTED_BIT);
-		}
-		out++;
-	}
-	__syncthreads();
-	if (threadIdx.x == 0) *sv.load_queue_count = s_total;  // may exceed q, consumers clamp (kernel.cu:409)
 }
 
 // emptiness bitmap: one warp per word (32 consecutive blocks in x), bit set iff any index word of the block is non-zero;
@@ -626,6 +601,10 @@ struct bm_context {
 	int run_len = 1;          // BRICKMAP_B200_RUN_LEN (1: 2723, 2: 2666, 4: 2503, 8: 2215, 16: 1683 Mrays/s -- the runs a warp still holds when the pool runs dry are the frame's tail)
 	int resume_at = 32;       // BRICKMAP_B200_RESUME_AT
 	int descending = 0;       // BRICKMAP_B200_DESCENDING: hand out slot runs from the end of the frame
+	// scratch of bm_requests_merge (sized for world * queue entries on first use)
+	uint32_t *m_keys = nullptr, *m_vals = nullptr, *m_keys_sorted = nullptr, *m_vals_sorted = nullptr, *m_first = nullptr, *m_place = nullptr;
+	void* m_cub = nullptr;
+	size_t m_cub_bytes = 0, m_entries = 0;
 	int q_blocks = 0;
 	bool q_stock = false;
 	size_t q_smem = 0, q_smem_record = 0;
@@ -728,6 +707,7 @@ void bm_destroy(bm_context* c) {
 	cudaFree(c->d_coarse);
 	cudaFree(c->d_fine);
 	cudaFree(c->d_flag);
+	cudaFree(c->m_keys); cudaFree(c->m_vals); cudaFree(c->m_keys_sorted); cudaFree(c->m_vals_sorted); cudaFree(c->m_first); cudaFree(c->m_place); cudaFree(c->m_cub);
 	for (cudaEvent_t e : c->events) cudaEventDestroy(e);
 	if (c->stream) cudaStreamDestroy(c->stream);
 	delete c;
@@ -814,7 +794,7 @@ int bm_scene_bind(bm_context* c, bm_gpu_scene scene) {
 		const uint64_t nb = ((uint64_t)(sv.cells + (1 << shift) - 1) >> shift) + 2, nz = ((uint64_t)(sv.cells_height + (1 << shift) - 1) >> shift) + 2;
 		roww = (nb + 31) / 32;
 		nby = nb;
-		words = nz * nb * roww;
+		words = (nz * nb * roww + 3) & ~(uint64_t)3;  // a multiple of 16 bytes: the bulk-copy granularity (stage_bitmap); the pad words are never addressed
 		if (words * 4 <= 64u * 1024u) break;
 	}
 	sv.coarse_shift = shift;
@@ -1161,6 +1141,31 @@ int bm_render(bm_context* c, float* blit, uint32_t frames, uint64_t target_paths
 	return 0;
 }
 
+int bm_extend_primaries(bm_context* c, bm_ray* queue, uint32_t frames, int sync) {
+	if (!c || !queue) return fail_api(BM_E_INVALID, "bm_extend_primaries: null argument");
+	if (!c->bound) return fail_api(BM_E_STATE, "bm_extend_primaries: no scene bound (bm_scene_bind)");
+	CK(cudaSetDevice(c->cfg.device));
+	// every frame starts from an empty survivor set and leaves one (nothing is shaded)
+	CK(cudaMemsetAsync(&c->d_state->primary_ray_cnt, 0, 4, c->stream));
+	int rc = clear_private_sets(c);
+	if (rc) return rc;
+	c->private_valid = true;
+	c->caller_survivors = 0;
+	begin_kernel<<<1, 1, 0, c->stream>>>(c->d_state, 0ull, 0u, c->cfg.ray_queue_buffer_size);
+	CK(cudaGetLastError());
+	c->launches += 1;
+	FrameIO io = private_io(c, nullptr);
+	io.record = queue;
+	io.shadow_mask = c->d_shadow_mask;
+	io.extend_only = 1u;
+	for (uint32_t f = 0; f < frames; f++) {
+		rc = launch_frame_kernels<true>(c, io, false);
+		if (rc) return rc;
+	}
+	if (sync) CK(cudaStreamSynchronize(c->stream));
+	return 0;
+}
+
 int bm_import_rays(bm_context* c, const bm_ray* queue, uint32_t count) {
 	if (!c || (count && !queue) || count > c->cfg.ray_queue_buffer_size) return fail_api(BM_E_INVALID, "bm_import_rays: bad argument");
 	CK(cudaSetDevice(c->cfg.device));
@@ -1212,12 +1217,35 @@ int bm_requests_merge(bm_context* c, const int32_t* gathered, int world) {
 	if (!c || !gathered || world < 1) return fail_api(BM_E_INVALID, "bm_requests_merge: bad argument");
 	if (!c->bound) return fail_api(BM_E_STATE, "bm_requests_merge: no scene bound (bm_scene_bind)");
 	CK(cudaSetDevice(c->cfg.device));
-	const size_t smem = (size_t)world * c->sv.queue_size * 4 * sizeof(int32_t);
-	if (smem > 200 * 1024) return fail_api(BM_E_INVALID, "bm_requests_merge: world_size * queue_size too large for one block");
-	CK(cudaFuncSetAttribute(requests_merge_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-	requests_merge_kernel<<<1, 1024, smem, c->stream>>>(c->sv, gathered, world);
+	const size_t n = (size_t)world * c->sv.queue_size;
+	if (n > (size_t)1 << 30) return fail_api(BM_E_INVALID, "bm_requests_merge: world_size * queue_size too large");
+	if ((uint64_t)c->sv.cells * c->sv.cells * c->sv.cells_height >= 0xFFFFFFFFull) return fail_api(BM_E_INVALID, "bm_requests_merge: world too large for 32-bit cell keys");
+	if (n > c->m_entries) {
+		cudaFree(c->m_keys); cudaFree(c->m_vals); cudaFree(c->m_keys_sorted); cudaFree(c->m_vals_sorted); cudaFree(c->m_first); cudaFree(c->m_place); cudaFree(c->m_cub);
+		c->m_keys = c->m_vals = c->m_keys_sorted = c->m_vals_sorted = c->m_first = c->m_place = nullptr;
+		c->m_cub = nullptr;
+		c->m_entries = 0;
+		CK(cudaMalloc(&c->m_keys, n * 4)); CK(cudaMalloc(&c->m_vals, n * 4)); CK(cudaMalloc(&c->m_keys_sorted, n * 4));
+		CK(cudaMalloc(&c->m_vals_sorted, n * 4)); CK(cudaMalloc(&c->m_first, n * 4)); CK(cudaMalloc(&c->m_place, n * 4));
+		size_t a = 0, b = 0;
+		CK(cub::DeviceRadixSort::SortPairs(nullptr, a, c->m_keys, c->m_keys_sorted, c->m_vals, c->m_vals_sorted, (int)n));
+		CK(cub::DeviceScan::ExclusiveSum(nullptr, b, c->m_first, c->m_place, (int)n));
+		c->m_cub_bytes = a > b ? a : b;
+		CK(cudaMalloc(&c->m_cub, c->m_cub_bytes ? c->m_cub_bytes : 16));
+		c->m_entries = n;
+	}
+	const unsigned blocks = (unsigned)((n + 255) / 256);
+	size_t bytes = c->m_cub_bytes;
+	merge_keys_kernel<<<blocks, 256, 0, c->stream>>>(c->sv, gathered, world, c->m_keys, c->m_vals);
 	CK(cudaGetLastError());
-	c->launches += 1;
+	CK(cub::DeviceRadixSort::SortPairs(c->m_cub, bytes, c->m_keys, c->m_keys_sorted, c->m_vals, c->m_vals_sorted, (int)n, 0, 32, c->stream));
+	merge_heads_kernel<<<blocks, 256, 0, c->stream>>>(c->m_keys_sorted, c->m_vals_sorted, (uint32_t)n, c->m_first);
+	CK(cudaGetLastError());
+	bytes = c->m_cub_bytes;
+	CK(cub::DeviceScan::ExclusiveSum(c->m_cub, bytes, c->m_first, c->m_place, (int)n, c->stream));
+	merge_write_kernel<<<blocks, 256, 0, c->stream>>>(c->sv, gathered, world, c->m_first, c->m_place);
+	CK(cudaGetLastError());
+	c->launches += 3;
 	return 0;
 }
 

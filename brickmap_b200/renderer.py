@@ -239,6 +239,10 @@ class Renderer:
         """Fused throughput path: `frames` frames (or until target_paths paths finished) into blit_buffer (device tensor)."""
         check(self.lib.bm_render(self.h, blit_buffer.data_ptr(), frames, target_paths, flags, 1 if sync else 0), "bm_render")
 
+    def extend_primaries(self, queue, frames=1, sync=True):
+        """Primary rays only (kernel.cu:416-418): post-extend records of all slots into `queue` (device tensor, RayQueue[n])."""
+        check(self.lib.bm_extend_primaries(self.h, queue.data_ptr(), frames, 1 if sync else 0), "bm_extend_primaries")
+
     def import_rays(self, rays):
         """Make `rays` (numpy RAY_DTYPE records) the survivor set the next render() starts from."""
         dev = torch.device("cuda", self.cfg.device)

@@ -189,6 +189,12 @@ int bm_launch_frame(bm_context* ctx, float* blit_buffer_device, bm_ray* queue_de
  * (BM_E_STATE otherwise); bm_launch_frame takes them from `queue` instead. */
 int bm_render(bm_context* ctx, float* blit_buffer_device, uint32_t frames, uint64_t target_paths, uint32_t flags, int sync);
 
+/* Primary visibility (BASELINE config 2, "primary rays only"): `frames` times primary_rays -> set_wavefront_globals -> extend
+ * (kernel.cu:416-418) over all ray_queue_buffer_size slots, every frame from an empty survivor set; nothing is shaded, the
+ * accumulation buffer is not touched. queue_device receives the post-extend record of every slot (of the last frame): origin,
+ * direction, hit normal and distance (1e20 = miss). Cursor and frame number advance as in bm_launch_frame. */
+int bm_extend_primaries(bm_context* ctx, bm_ray* queue_device, uint32_t frames, int sync);
+
 /* Hand the throughput path an explicit survivor set: `count` dense records (the layout bm_launch_frame leaves in queue2) become
  * the survivors of the previous frame, primary_ray_cnt = count. bm_export_rays is the inverse: the current private survivor set,
  * densely, in slot order (what the reference would hold in ray_buffer_next[0, primary_ray_cnt)). */

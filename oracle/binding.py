@@ -316,6 +316,8 @@ class Reference:
         L.ref_host_supercell.argtypes = [C.c_int, C.c_void_p, C.c_void_p]
         if not variant.startswith("dropin_"):
             L.ref_run_stage.argtypes = [C.c_int, C.c_int, C.c_uint, C.c_int]
+            if hasattr(L, "ref_run_primary_extend"):
+                L.ref_run_primary_extend.argtypes = [C.c_int, C.c_uint, C.c_void_p]
             L.ref_eval_sky.argtypes = [C.c_int, C.c_void_p, C.c_int, C.c_void_p]
             L.ref_read_counters.argtypes = [C.c_void_p]
             L.ref_write_counters.argtypes = [C.c_void_p]
@@ -385,6 +387,12 @@ class Reference:
         shadows = C.c_uint64()
         self._chk(self.lib.ref_run_frames(frames, 1 if process_queue else 0, C.byref(ms), C.byref(shadows)))
         return float(ms.value), int(shadows.value)
+
+    def run_primary_extend(self, frames, first_frame=1):
+        """primary_rays + set_wavefront_globals + extend (kernel.cu:416-418), `frames` times; returns device milliseconds."""
+        ms = C.c_float()
+        self._chk(self.lib.ref_run_primary_extend(frames, first_frame, C.byref(ms)))
+        return float(ms.value)
 
     def counters(self):
         out = np.zeros(7, np.uint32)

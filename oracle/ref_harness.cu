@@ -327,6 +327,35 @@ int ref_run_stage(int stage, int serial, unsigned int frame, int upload_count) {
 	return 0;
 }
 
+// Reference arm of BASELINE config 2 (primary rays only): `frames` times primary_rays -> set_wavefront_globals -> extend
+// (kernel.cu:416-418) with the stock launch shapes, CUDA-event timed, no host synchronisation in between. The survivor count
+// is zeroed before every frame, so that each frame generates and extends ray_queue_buffer_size fresh primaries.
+int ref_run_primary_extend(int frames, unsigned int first_frame, float* ms_out) {
+	glm::vec3 right, up;
+	camera_basis(right, up);
+	const int blocks = sm_cores * 8, threads = 128;
+	const uint32_t w = (uint32_t)g_state->screen_width, h = (uint32_t)g_state->screen_height;
+	cudaEvent_t e0, e1;
+	HCHECK(cudaEventCreate(&e0));
+	HCHECK(cudaEventCreate(&e1));
+	const unsigned int zero = 0;
+	HCHECK(cudaDeviceSynchronize());
+	HCHECK(cudaEventRecord(e0, 0));
+	for (int f = 0; f < frames; f++) {
+		HCHECK(cudaMemcpyToSymbolAsync(primary_ray_cnt, &zero, 4, 0, cudaMemcpyHostToDevice, 0));
+		primary_rays<<<blocks, threads>>>(g_state->ray_buffer_work, right, up, camera.direction, camera.position, first_frame + f, camera.focalDistance, camera.lensRadius, g_scene->gpuScene, g_state->blit_buffer, camera.position, w, h);
+		set_wavefront_globals<<<1, 1>>>(w, h);
+		extend<<<blocks, threads>>>(g_state->ray_buffer_work, g_scene->gpuScene, camera.position / 8.f);
+	}
+	HCHECK(cudaEventRecord(e1, 0));
+	HCHECK(cudaEventSynchronize(e1));
+	HCHECK(cudaEventElapsedTime(ms_out, e0, e1));
+	HCHECK(cudaGetLastError());
+	cudaEventDestroy(e0);
+	cudaEventDestroy(e1);
+	return 0;
+}
+
 #endif  // !BM_DROPIN
 
 int ref_read_load_queue(uint32_t* count, int* positions /* 3*brick_load_queue_size */) {

@@ -531,6 +531,15 @@ def test_extend_only_matches_reference_golden(golden, stores):
     c = ren.counters()
     assert [c.primary_ray_cnt, c.shadow_ray_cnt, c.start_position, c.frame] == [0, 0, int(g["f1_counters"][2]), 2]
     assert float(state.blit_buffer.abs().sum()) == 0.0
+    # the throughput form of the same thing: frames back to back, the queue holds the last frame's records
+    ren2 = renderer_for(g, store)
+    q = torch.zeros(store.cfg.ray_queue_buffer_size * 16, dtype=torch.float32, device="cuda")
+    ren2.extend_primaries(q, 1)
+    rec = q.cpu().numpy().view(np.uint8).view(bm.RAY_DTYPE)
+    assert_records_equal(rec[g["f1_ext_idx"]], g["f1_ext"], what="post-extend records, bm_extend_primaries")
+    ren2.extend_primaries(q, 2)
+    c = ren2.counters()
+    assert [c.primary_ray_cnt, c.frame] == [0, 4] and ren2.stats()["extend_rays"] == 3 * store.cfg.ray_queue_buffer_size
 
 
 def _check_tile_against_oracle(oracle, g, store_for, tile_kw, tile, frames=3):
@@ -638,6 +647,50 @@ def test_streaming_matches_oracle_as_sets(oracle, golden, stores):
     assert_close_rel(state.blit_buffer.cpu().numpy(), oren.accum, RADIANCE_TOL, "accumulation while streaming")
 
 
+def test_streaming_with_a_large_queue_matches_oracle(oracle, lib):
+    """brick_load_queue_size is a real parameter: 16 384 here (the reference's 1024, variables.h:35, needs 12 frames for what this
+    view requests in one). 12 k requests in frame 1: request sets, index words (slot bits masked: the queue order of a parallel run
+    is scheduling-dependent), slot numbers dense per superchunk, brick contents through the indirection, radiance.
+    Exercises the sort-based streaming step (bm_scene_store_stream) far beyond one block's worth of requests."""
+    q = 16384
+    cfg = bm.default_config(grid_size=1024, grid_height=256, brick_load_queue_size=q, ray_queue_buffer_size=262144, screen_width=640, screen_height=360)
+    store = bm.SceneStore(cfg, resident=False)
+    osc = ob.OracleScene(oracle, 1024, 256, cfg.lod_distance_2x2x2, cfg.lod_distance_8x8x8, q).generate_terrain()
+    d = np.array([0.5, 0.6, -0.62], np.float32)
+    d = (d / np.sqrt((d.astype(np.float64) ** 2).sum())).astype(np.float32)
+    pos = (100.0, 80.0, 420.0)
+    ren = bm.Renderer(cfg, store)
+    ren.set_camera(bm.make_camera(position=pos, direction=d))
+    oren = ob.OracleRenderer(osc, 640, 360, 262144, ob.make_camera(position=pos, direction=d))
+    state = bm.State(cfg)
+    counts = []
+    for f in range(1, 5):
+        ren.launch_kernels(state)
+        cnt, rpos = ren.load_queue()
+        staged = store.process_load_queue(ren.stream, want_count=True)
+        state.swap()
+        if f > 1:
+            osc.stream()
+        oren.frame(threads=1)
+        ocnt, opos = osc.queue()
+        assert cnt == ocnt <= q and staged == cnt
+        assert sorted(map(tuple, rpos)) == sorted(map(tuple, opos)), "frame %d request sets differ" % f
+        counts.append(cnt)
+        c = ren.counters()
+        assert [c.primary_ray_cnt, c.shadow_ray_cnt] == [oren.state.primary_ray_cnt, oren.state.shadow_ray_cnt]
+    assert counts[0] > 8 * 1024, "the view must request far more than the reference's queue holds"
+    ren.synchronize()
+    for sc in range(store.superchunks):
+        mine, want = store.indices(sc), osc.gpu_indices(sc)
+        assert np.array_equal(mine & ~np.uint32(0xFFF), want & ~np.uint32(0xFFF)), "index words (slot bits masked) differ in superchunk %d" % sc
+        loaded = np.flatnonzero(mine & 0x80000000)
+        if loaded.size:
+            assert sorted(mine[loaded] & 0xFFF) == list(range(loaded.size)), "slots of superchunk %d are not 0..n-1" % sc
+            gb = store.bricks(sc, gpu_view=True)
+            for cell in loaded[:: max(1, loaded.size // 8)]:
+                assert np.array_equal(gb[mine[cell] & 0xFFF], osc.gpu_brick(sc, int(want[cell] & 0xFFF))), "brick content through the indirection"
+
+
 def test_streaming_serial_order_matches_reference_golden(golden):
     """Frame 1 of the reference's streaming fixture: the request SET of an all-unloaded scene."""
     g = golden("256")
@@ -683,6 +736,41 @@ def test_request_merge_kernel_matches_specification(golden):
         return idx[sc][(p[0] & 15) + (p[1] & 15) * 16 + (p[2] & 15) * 256]
     assert all(word(p) & 0x20000000 for p in kept), "kept requests carry the requested bit"
     assert not any(word(p) & 0x20000000 for p in dropped), "dropped requests are released for a later frame"
+
+
+def test_request_merge_kernel_at_eight_ranks_and_a_large_queue():
+    """The merge at the sizes the multi-GPU benchmark and BASELINE config 4 need (8 ranks x 16 384 entries: far beyond one block's
+    shared memory, where round 1's kernel stopped), duplicates within and across ranks, against the specification function."""
+    from brickmap_b200.parallel import merge_request_blocks
+    q, world = 16384, 8
+    cfg = bm.default_config(grid_size=1024, grid_height=256, brick_load_queue_size=q, ray_queue_buffer_size=65536, screen_width=64, screen_height=64)
+    store = bm.SceneStore(cfg, resident=False)
+    ren = bm.Renderer(cfg, store)
+    rng = np.random.default_rng(5)
+    idx = np.concatenate([store.indices(sc) for sc in range(store.superchunks)])
+    nz = np.flatnonzero(idx)
+    sc_, loc = nz // 4096, nz % 4096
+    sx, sy, sz = sc_ % 8, (sc_ // 8) % 8, sc_ // 64
+    cells = np.stack([sx * 16 + (loc & 15), sy * 16 + ((loc >> 4) & 15), sz * 16 + (loc >> 8)], axis=1).astype(np.int32)
+    pool = cells[rng.choice(len(cells), size=40000, replace=False)]
+    blocks = np.zeros((world, 1 + 3 * q), np.int32)
+    for r in range(world):
+        n = [16384, 9000, 0, 16384, 1, 12000, 16384, 7777][r]
+        pick = pool[rng.integers(0, len(pool), n)]  # with repetitions, inside and across ranks
+        blocks[r, 0] = n if r != 3 else n + 500  # a count beyond the queue size is clamped (kernel.cu:409)
+        blocks[r, 1:1 + 3 * n] = pick.reshape(-1)
+    total, kept, dropped = merge_request_blocks(blocks, q)
+    assert total > q and len(kept) == q and len(dropped) > 0
+    dev = torch.as_tensor(blocks, device="cuda")
+    assert bm.load().bm_requests_merge(ren.h, dev.data_ptr(), world) == 0
+    cnt, pos = ren.load_queue()
+    assert cnt == total and np.array_equal(pos, kept)
+    idx2 = np.concatenate([store.indices(sc) for sc in range(store.superchunks)])
+
+    def words(p):
+        sc = (p[:, 0] >> 4) + (p[:, 1] >> 4) * 8 + (p[:, 2] >> 4) * 64
+        return idx2[sc * 4096 + (p[:, 0] & 15) + (p[:, 1] & 15) * 16 + (p[:, 2] & 15) * 256]
+    assert np.all(words(kept) & 0x20000000) and not np.any(words(dropped) & 0x20000000)
 
 
 # ---- caves world (BASELINE config 4 at a size the oracle can build) + LoD + tone map ------------------------------------
@@ -737,6 +825,57 @@ def test_tonemap_matches_oracle(oracle, golden, stores):
     ok = acc[..., 3] > 0
     assert ok.mean() > 0.9
     assert_close_rel(got[ok], want[ok], 1e-5, "tone-mapped image")
+
+
+@pytest.mark.parametrize("view", [1, 4, 5, 6, 7, 8])
+def test_camera_tour_views_match_oracle(oracle, golden, stores, view):
+    """The reference's benchmark views (performance_measure.h:4-25; brickmap_b200/views.py). Views 4-8 stand outside the stock
+    world: every primary ray enters through the AABB (voxel.cuh:142-155, never suspended in the throughput kernel) and the far
+    cells are 8x8x8 boxes (voxel.cuh:212-214). Two frames through both entry points against the oracle."""
+    from brickmap_b200.views import tour
+    g = golden("4096")
+    pos, d = tour()[view]
+    w, h, n = 320, 180, 65536
+    cfg = cfg_from_golden(g)
+    cfg.screen_width, cfg.screen_height, cfg.ray_queue_buffer_size = w, h, n
+    store = stores("4096")
+    ren = bm.Renderer(cfg, store)
+    ren.set_camera(bm.make_camera(position=pos, direction=d))
+    fused = bm.Renderer(cfg, store)
+    fused.set_camera(bm.make_camera(position=pos, direction=d))
+    s = _oracle_scene_4096(oracle)
+    oren = ob.OracleRenderer(s, w, h, n, ob.make_camera(position=pos, direction=d))
+    state = bm.State(cfg)
+    for f in range(2):
+        ren.launch_kernels(state)
+        oren.primary_rays()
+        oren.set_wavefront_globals()
+        oren.extend()
+        ext = oren.rays.copy()
+        oren.shade()
+        oren.connect()
+        oren.state.frame += 1
+        oren.rays, oren.next = oren.next, oren.rays
+        c = ren.counters()
+        assert [c.primary_ray_cnt, c.shadow_ray_cnt] == [oren.state.primary_ray_cnt, oren.state.shadow_ray_cnt]
+        assert_records_equal(state.rays("work"), ext, what="view %d frame %d post-extend" % (view, f + 1))
+        assert_records_equal(state.rays("next", c.primary_ray_cnt), oren.rays[: c.primary_ray_cnt], what="view %d frame %d survivors" % (view, f + 1))
+        state.swap()
+    if view in (1, 4):  # (view 7 looks past the world: sky only, like in the reference's tour)
+        assert oren.stats.hits > 0, "the view must see the world"
+    assert_close_rel(state.blit_buffer.cpu().numpy(), oren.accum, RADIANCE_TOL, "view %d accumulation" % view)
+    blit = torch.zeros(h, w, 4, dtype=torch.float32, device="cuda")
+    fused.render(blit, 2)
+    assert_close_rel(blit.cpu().numpy(), oren.accum, RADIANCE_TOL, "view %d accumulation, fused path" % view)
+
+
+_ORACLE_4096 = []
+
+
+def _oracle_scene_4096(oracle):
+    if not _ORACLE_4096:
+        _ORACLE_4096.append(ob.OracleScene(oracle, 4096, 512).generate_terrain().set_residency(True))
+    return _ORACLE_4096[0]
 
 
 # ---- against the live reference -------------------------------------------------------------------------------------
@@ -831,3 +970,42 @@ def test_reference_host_main_loop_on_new_kernels(golden, tmp_path):
     rm, dm = tile_means(ra), tile_means(da)
     rel = np.abs(dm[..., :3] / dm[..., 3:] - rm[..., :3] / rm[..., 3:]) / np.maximum(rm[..., :3] / rm[..., 3:], 1e-6)
     assert np.median(rel) < 0.02 and rel.max() < 0.15
+
+
+@pytest.mark.skipif(not ob.Reference.available("4096"), reason="oracle/_ref not built")
+def test_statistical_parity_at_the_benchmark_config(golden, stores):
+    """P3 of SURVEY 8c at BASELINE config 3 itself: 1920x1080, 16 spp, stock world, benchmark camera. The reference's normal
+    parallel run (non-deterministic slot order after frame 1) and bm_render converge to the same image: per-tile mean radiance
+    (8x8 tiles of 240x135 pixels, ~0.5 M paths each) within Monte-Carlo noise."""
+    g = golden("4096")
+    w, h = int(g["width"]), int(g["height"])
+    target = 16 * w * h
+    ref = ob.Reference("4096", w, h)
+    import os
+    import sys
+    sys.stdout.flush()
+    saved = os.dup(1)
+    os.dup2(2, 1)
+    try:
+        ref.generate()
+    finally:
+        os.dup2(saved, 1)
+        os.close(saved)
+    ref.force_resident()
+    ref.set_camera(ob.make_camera(position=g["cam_pos"], direction=g["cam_dir"]))
+    ref.set_sun(float(g["sun"][0]), float(g["sun"][1]))
+    frames = 0
+    while ref.alpha_sum() < target and frames < 64:
+        ref.run_frames(1)
+        frames += 1
+    r = ref.read_accum()
+    ren = renderer_for(g, stores("4096"))
+    blit = torch.zeros(h, w, 4, dtype=torch.float32, device="cuda")
+    ren.render(blit, 64, target_paths=target)
+    m = blit.cpu().numpy()
+    assert abs(ren.stats()["frames"] - frames) <= 1
+    assert abs(m[..., 3].sum() / r[..., 3].sum() - 1) < 0.04
+    rm, mm = tile_means(r), tile_means(m)
+    ra, ma = rm[..., :3] / rm[..., 3:], mm[..., :3] / mm[..., 3:]
+    rel = np.abs(ma - ra) / np.maximum(ra, 1e-6)
+    assert np.median(rel) < 0.005 and rel.max() < 0.03, "tile means differ: median %.4f max %.4f" % (np.median(rel), rel.max())

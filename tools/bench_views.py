@@ -17,15 +17,7 @@ import numpy as np
 
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 
-POSITIONS = [(512, 512, 300), (840.254, 832.446, 1169.88), (2227.83, 774.886, 204.955), (3326.19, 2055.72, 44.7995), (7134.6, 1262.44, 5531.79),
-             (11298.6, 3113.03, 598.019), (10921.4, 4774.14, 267.808), (9961.29, 4508.12, 189.59), (10835.3, 4160.83, 359.992)]
-ANGLES = [(-61863.5, -0.501796), (-61864.4, -0.429796), (-61863.9, 0.0622036), (-61864.2, -0.981796), (-61865.2, -0.501796), (-61866.3, -0.141796),
-          (-61859.4, 0.0142036), (-61857.2, -0.261796)]
-
-
-def direction(h, v):  # Camera::update, camera.cpp:48-54 (double precision trigonometry, then float)
-    d = np.array([math.cos(v) * math.sin(h), math.cos(v) * math.cos(h), math.sin(v)], np.float32)
-    return (d * np.float32(1.0 / np.sqrt(np.float32(d[0] * d[0] + d[1] * d[1] + d[2] * d[2])))).astype(np.float32)
+from brickmap_b200.views import ANGLES, POSITIONS, direction  # noqa: E402
 
 
 def main():
