@@ -74,13 +74,6 @@ def measured_peaks():
         return 6650.0, "fallback"
 
 
-def git_head():
-    try:
-        return subprocess.check_output(["git", "-C", ROOT, "rev-parse", "--short", "HEAD"], stderr=subprocess.DEVNULL, text=True).strip()
-    except Exception:
-        return None
-
-
 class ClockSampler:
     """nvidia-smi clocks/throttle reasons sampled DURING the timed region (B200_PROFILING.md)."""
     Q = "index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
@@ -540,12 +533,13 @@ def main():
     # and the config it was taken on); a capture of another tree, another config or another GPU count does not describe this run
     traffic, traffic_note = None, "no ncu capture for this tree / config / GPU count"
     try:
+        from brickmap_b200.build import source_hash
         with open(os.path.join(ROOT, "profiles", "frame_kernel_traffic.json")) as f:
             tj = json.load(f)
-        if tj.get("commit") and tj.get("commit") == git_head() and tj.get("config", "cfg3") == args.config and world == 1:
-            traffic, traffic_note = tj.get("dram_bytes_per_launch"), "ncu --set full capture of one launch, commit %s" % tj["commit"]
-        elif tj.get("commit") and world == 1 and tj.get("config", "cfg3") == args.config:
-            traffic_note = "capture is from commit %s, this tree is %s" % (tj["commit"], git_head())
+        if tj.get("source_hash") == source_hash() and tj.get("config") == args.config and world == 1:
+            traffic, traffic_note = tj.get("dram_bytes_per_launch"), "ncu --set full capture of one launch of these kernel sources (hash %s)" % tj["source_hash"]
+        elif tj.get("config") == args.config and world == 1:
+            traffic_note = "the committed capture describes kernel sources %s, this tree is %s" % (tj.get("source_hash"), source_hash())
     except Exception:
         pass
     roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": (achieved / peak) if achieved else None, "traffic": traffic,

@@ -18,6 +18,16 @@ NVCC_FLAGS = (["-DBM_QDEBUG"] if os.environ.get("BM_QDEBUG") else []) + ["-std=c
               "-Xcompiler", "-fPIC", "-shared"]
 
 
+def source_hash():
+    """sha256 (first 12 hex digits) over the kernel sources: stamps measurements that describe one build (profiles/frame_kernel_traffic.json)."""
+    import hashlib
+    h = hashlib.sha256()
+    for name in sorted(SOURCES + HEADERS):
+        with open(os.path.join(CSRC, name), "rb") as f:
+            h.update(f.read())
+    return h.hexdigest()[:12]
+
+
 def needs_build():
     if not os.path.exists(LIB):
         return True

@@ -12,7 +12,7 @@
 
 #include "../../include/brickmap_b200.h"
 
-extern __shared__ uint32_t bm_dyn_smem[];  // the kernels' dynamic shared memory starts with their copy of the emptiness bitmap
+extern __shared__ __align__(16) uint32_t bm_dyn_smem[];  // the kernels' dynamic shared memory starts with their copy of the emptiness bitmap
 
 namespace bm {
 
@@ -257,20 +257,76 @@ __device__ __forceinline__ bool intersect_byte(const F3& origin, const F3& direc
 	return false;
 }
 
-// voxel.cuh:79-133 (8x8x8 voxel brick). The 64-byte brick is fetched once as four 128-bit loads; the DDA then
-// tests bits of the 8 z-slices held in registers instead of one dependent 4-byte global load per step.
+// voxel.cuh:79-133 (8x8x8 voxel brick). The 64 bits of the z-slice the DDA stands in are kept in a register pair and reloaded only
+// when the step goes along z, so two steps out of three test a bit without a load in their dependent chain.
+// BM_BRICK_PTX=1: the whole walk is ONE block of PTX. What that buys over the C++ form (29 -> 20 SASS instructions per voxel step,
+// profiles/r2_sass_loops.txt): the step's predicates stay live, so (1) the slice reload is two instructions predicated on "stepped
+// along z" instead of compare + branch + reconvergence, (2) the stepped axis is materialised once, at the hit, instead of two selects
+// per step, (3) the bit test is a 64-bit funnel shift + one predicate-setting AND.
+#ifndef BM_BRICK_PTX
+#define BM_BRICK_PTX 0
+#endif
 __device__ __forceinline__ bool intersect_brick(const F3& origin, const F3& direction, const Dda& parent, F3& normal, float& distance, const bm_brick* brick) {
 	Dda a;
 	dda_setup_nested(origin, direction, parent, a);
-	const I3 lim{ 8, 8, 8 };
 	// The remainders cannot be negative: origin = 8 x - n eps with x inside a cell of the world, so every component is > -1 and
 	// truncates to >= 0 (the reference would index out of the brick otherwise, voxel.cuh:103,110-113); & 7 == % 8 then.
 	a.pos = I3{ a.pos.x & 7, a.pos.y & 7, a.pos.z & 7 };
 	distance = 0.f;
 	int step_axis = -1;
-	// The 64 bits of the z-slice the DDA stands in are kept in registers and reloaded only when z changes: two steps out of
-	// three test a bit without a load in their dependent chain (the walk runs with few lanes and is latency-bound).
 	const uint2* slices = reinterpret_cast<const uint2*>(brick->data);  // bricks are 64-byte aligned (Scene.cpp:170-176)
+#if BM_BRICK_PTX
+	const unsigned long long first = __ldg(reinterpret_cast<const unsigned long long*>(slices) + a.pos.z);
+	if ((first >> (a.pos.x + a.pos.y * 8)) & 1ull) return true;  // the ray starts in a solid voxel: normal and distance stay (voxel.cuh:114-119)
+	uint32_t hit;
+	asm volatile(
+	    "{\n\t"
+	    ".reg .pred pxy, mx, my, mz, pout, pbit;\n\t"
+	    ".reg .b32 bit, any, w;\n\t"
+	    ".reg .b64 addr, slice, sh;\n\t"
+	    "mov.b64 slice, %8;\n\t"
+	    "BM_BRICK_STEP:\n\t"
+	    "setp.lt.f32 pxy, %3, %4;\n\t"                 // voxel.cuh:122-126, see dda_advance
+	    "setp.lt.and.f32 mx, %3, %5, pxy;\n\t"
+	    "setp.lt.and.f32 my, %4, %5, !pxy;\n\t"
+	    "or.pred mz, mx, my;\n\t"
+	    "not.pred mz, mz;\n\t"
+	    "@mx add.s32 %0, %0, %9;\n\t"
+	    "@my add.s32 %1, %1, %10;\n\t"
+	    "@mz add.s32 %2, %2, %11;\n\t"
+	    "@mx add.rn.f32 %3, %3, %12;\n\t"
+	    "@my add.rn.f32 %4, %4, %13;\n\t"
+	    "@mz add.rn.f32 %5, %5, %14;\n\t"
+	    "or.b32 any, %0, %1;\n\t"                        // left the brick: some coordinate is -1 or 8 (voxel.cuh:128)
+	    "or.b32 any, any, %2;\n\t"
+	    "setp.gt.u32 pout, any, 7;\n\t"
+	    "@pout bra BM_BRICK_MISS;\n\t"
+	    "@!mz bra BM_BRICK_SAME_SLICE;\n\t"              // (ptxas turns a predicated load into a branch anyway; this way the address
+	    "mad.wide.u32 addr, %2, 8, %15;\n\t"             //  arithmetic sits behind it too)
+	    "ld.global.nc.u64 slice, [addr];\n\t"
+	    "BM_BRICK_SAME_SLICE:\n\t"
+	    "mad.lo.s32 bit, %1, 8, %0;\n\t"                 // voxel.cuh:110-113
+	    "shr.u64 sh, slice, bit;\n\t"
+	    "cvt.u32.u64 w, sh;\n\t"
+	    "and.b32 w, w, 1;\n\t"
+	    "setp.ne.u32 pbit, w, 0;\n\t"
+	    "@!pbit bra BM_BRICK_STEP;\n\t"
+	    "selp.s32 %6, 0, 2, mx;\n\t"                     // hit: the axis of the step that led here
+	    "@my mov.s32 %6, 1;\n\t"
+	    "mov.u32 %7, 1;\n\t"
+	    "bra BM_BRICK_DONE;\n\t"
+	    "BM_BRICK_MISS:\n\t"
+	    "mov.u32 %7, 0;\n\t"
+	    "BM_BRICK_DONE:\n\t"
+	    "}"
+	    : "+r"(a.pos.x), "+r"(a.pos.y), "+r"(a.pos.z), "+f"(a.tmax.x), "+f"(a.tmax.y), "+f"(a.tmax.z), "+r"(step_axis), "=r"(hit)
+	    : "l"(first), "r"(a.stepi.x), "r"(a.stepi.y), "r"(a.stepi.z), "f"(a.tdelta.x), "f"(a.tdelta.y), "f"(a.tdelta.z), "l"(slices));
+	if (!hit) return false;
+	normal = axis_normal(a, step_axis);
+	distance = comp(a.tmax, step_axis) - comp(a.tdelta, step_axis);
+	return true;
+#else
+	const I3 lim{ 8, 8, 8 };
 	int cz = a.pos.z;
 	uint2 slice = __ldg(slices + cz);
 	for (;;) {
@@ -298,6 +354,7 @@ __device__ __forceinline__ bool intersect_brick(const F3& origin, const F3& dire
 		}
 	}
 	return false;
+#endif
 }
 
 // voxel.cuh:13-24
@@ -496,7 +553,7 @@ __device__ __forceinline__ bool intersect_voxel(const SceneView& sv, const uint3
 // and division steps of the sky model may use the hardware approximations (ex2.approx / rcp.approx / rsqrt.approx, <= 2 ulp each,
 // ~1e-6 relative on the result): BM_FAST_RADIANCE=1. Everything that decides a ray's geometry stays IEEE-exact.
 #ifndef BM_FAST_RADIANCE
-#define BM_FAST_RADIANCE 0
+#define BM_FAST_RADIANCE 1  // measured +2.1 % (profiles/r2_c_ab_bulk_fastrad.txt)
 #endif
 #if BM_FAST_RADIANCE
 __device__ __forceinline__ float r_exp(float x) { return __expf(x); }

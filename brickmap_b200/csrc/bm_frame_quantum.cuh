@@ -57,6 +57,9 @@ struct QSched {
 // The block's copy of the emptiness bitmap (46 KiB at reference dims). BM_BULK_PROLOGUE=1: ONE bulk asynchronous copy global -> shared
 // (cp.async.bulk, the 1-D form of TMA; SASS UBLKCP) issued by thread 0 and awaited by all threads on an mbarrier, instead of the
 // cooperative __ldg / st.shared loop. `words` is a multiple of 4 (16-byte granularity of the bulk copy), both addresses are 16-byte aligned.
+#ifndef BM_BULK_PROLOGUE
+#define BM_BULK_PROLOGUE 1  // same speed as the loop (2747 vs 2748 Mrays/s, profiles/r2_c_ab_bulk_fastrad.txt): kept as the B200-idiomatic form
+#endif
 __device__ __forceinline__ void stage_bitmap(uint32_t* s_coarse, const uint32_t* g_coarse, uint32_t words) {
 #if BM_BULK_PROLOGUE
 	__shared__ __align__(8) unsigned long long s_bar;
@@ -89,7 +92,7 @@ __device__ __forceinline__ void stage_bitmap(uint32_t* s_coarse, const uint32_t*
 template <bool STOCK, bool RECORD>
 __global__ void __launch_bounds__(kQBlock, 1) frame_kernel_q(const FrameParams fp, const SceneView sv, const FrameIO io, const QSched sch) {
 	const int quantum = sch.quantum, min_share = sch.min_share, descending = sch.descending, inline_tests = sch.inline_tests;
-	extern __shared__ uint32_t s_coarse[];
+	extern __shared__ __align__(16) uint32_t s_coarse[];
 	DeviceState* st = io.st;
 	if (st->done) return;
 	stage_bitmap(s_coarse, sv.coarse, sv.coarse_words);

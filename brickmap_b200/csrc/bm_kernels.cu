@@ -279,45 +279,86 @@ __global__ void __launch_bounds__(kTile, 4) frame_kernel(const FrameParams fp, c
 namespace bm {
 
 // set_wavefront_globals (kernel.cu:122-139) + per-tile survivor counts (popcount of the slot masks) -> exclusive prefix.
-// One block. mask[ntiles * 8] -> prefix[ntiles + 1]; optional second pair for the shadow queue (RECORD). Also zeroes
-// `clear_mask`, the mask buffer the NEXT frame will write with atomicOr.
-__global__ void __launch_bounds__(1024) scan_kernel(const FrameIO io, const uint32_t* shadow_mask, uint32_t* shadow_prefix, uint32_t ntiles, uint32_t n_slots,
-                                                     uint32_t pixels) {
-	__shared__ uint32_t s_part[1024];
+// mask[ntiles * 8] -> prefix[ntiles + 1]; optional second pair for the shadow queue (RECORD). Also zeroes the mask buffer the NEXT
+// frame will write with atomicOr. Multi-block: block b scans kScanTiles tiles (one per thread) and leaves its total; the block that
+// finishes last (ticket counter, no waiting anywhere) scans the block totals, adds the bases and advances the frame state.
+constexpr int kScanTiles = 256;
+__device__ __forceinline__ uint32_t tile_count(const uint32_t* mask, uint32_t tile) {
+	const uint4 lo = *reinterpret_cast<const uint4*>(mask + (size_t)tile * 8), hi = *reinterpret_cast<const uint4*>(mask + (size_t)tile * 8 + 4);
+	return __popc(lo.x) + __popc(lo.y) + __popc(lo.z) + __popc(lo.w) + __popc(hi.x) + __popc(hi.y) + __popc(hi.z) + __popc(hi.w);
+}
+// exclusive scan over the block's kScanTiles threads; returns the block total through `total`
+__device__ __forceinline__ uint32_t block_exclusive_scan(uint32_t v, uint32_t* s_warp /*kScanTiles / 32 + 1*/, uint32_t& total) {
+	const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+	uint32_t incl = v;
+#pragma unroll
+	for (int o = 1; o < 32; o <<= 1) {
+		const uint32_t u = __shfl_up_sync(0xFFFFFFFFu, incl, o);
+		if (lane >= (uint32_t)o) incl += u;
+	}
+	__syncthreads();  // s_warp may still be read from a previous call
+	if (lane == 31) s_warp[warp] = incl;
+	__syncthreads();
+	uint32_t base = 0, all = 0;
+#pragma unroll
+	for (int w = 0; w < kScanTiles / 32; w++) {
+		const uint32_t t = s_warp[w];
+		if (w < (int)warp) base += t;
+		all += t;
+	}
+	total = all;
+	return base + incl - v;
+}
+__global__ void __launch_bounds__(kScanTiles) scan_kernel(const FrameIO io, const uint32_t* shadow_mask, uint32_t* shadow_prefix, uint32_t ntiles, uint32_t n_slots,
+                                                           uint32_t pixels, uint32_t* block_totals /*2 * gridDim.x*/, uint32_t* ticket) {
+	__shared__ uint32_t s_warp[kScanTiles / 32 + 1];
+	__shared__ uint32_t s_last, s_carry;
 	DeviceState* st = io.st;
-	if (st->done) return;
+	if (st->done) return;          // (only the last block changes the state, after every other block has taken its ticket)
 	const uint32_t cur = st->cur;  // the set the frame kernel read; it wrote set cur ^ 1
 	const uint32_t* mask = cur ? io.mask[0] : io.mask[1];
 	uint32_t* prefix = cur ? io.prefix[0] : io.prefix[1];
 	uint32_t* clear_mask = cur ? io.mask[1] : io.mask[0];  // this frame's input becomes the next frame's output
-	__syncthreads();  // every thread has read st->cur before thread 0 toggles it below
-	const uint32_t per = (ntiles + blockDim.x - 1) / blockDim.x;
+	const uint32_t tile = blockIdx.x * kScanTiles + threadIdx.x;
 	for (int pass = 0; pass < 2; pass++) {
 		const uint32_t* in = pass == 0 ? mask : shadow_mask;
 		uint32_t* out = pass == 0 ? prefix : shadow_prefix;
 		if (!in) continue;
-		const uint32_t b = min(ntiles, threadIdx.x * per), e = min(ntiles, b + per);
-		uint32_t sum = 0;
-		for (uint32_t i = b; i < e; i++) {
-			const uint4 lo = *reinterpret_cast<const uint4*>(in + (size_t)i * 8), hi = *reinterpret_cast<const uint4*>(in + (size_t)i * 8 + 4);
-			sum += __popc(lo.x) + __popc(lo.y) + __popc(lo.z) + __popc(lo.w) + __popc(hi.x) + __popc(hi.y) + __popc(hi.z) + __popc(hi.w);
-		}
-		s_part[threadIdx.x] = sum;
+		const uint32_t n = tile < ntiles ? tile_count(in, tile) : 0u;
+		uint32_t total;
+		const uint32_t excl = block_exclusive_scan(n, s_warp, total);
+		if (tile < ntiles) out[tile] = excl;  // relative to the block; the last block adds the base
+		if (threadIdx.x == 0) block_totals[pass * gridDim.x + blockIdx.x] = total;
+	}
+	if (tile < ntiles) {
+		reinterpret_cast<uint4*>(clear_mask)[(size_t)tile * 2] = make_uint4(0, 0, 0, 0);
+		reinterpret_cast<uint4*>(clear_mask)[(size_t)tile * 2 + 1] = make_uint4(0, 0, 0, 0);
+	}
+	__threadfence();
+	__syncthreads();
+	if (threadIdx.x == 0) s_last = atomicAdd(ticket, 1u) == gridDim.x - 1 ? 1u : 0u;
+	__syncthreads();
+	if (!s_last) return;
+	__threadfence();
+	for (int pass = 0; pass < 2; pass++) {
+		uint32_t* out = pass == 0 ? prefix : shadow_prefix;
+		if (!(pass == 0 ? mask : shadow_mask)) continue;
+		uint32_t* totals = block_totals + pass * gridDim.x;
+		if (threadIdx.x == 0) s_carry = 0;
 		__syncthreads();
-		for (uint32_t off = 1; off < blockDim.x; off <<= 1) {  // Hillis-Steele inclusive scan of the partials
-			const uint32_t v = threadIdx.x >= off ? s_part[threadIdx.x - off] : 0;
+		for (uint32_t b0 = 0; b0 < gridDim.x; b0 += kScanTiles) {  // block totals -> block bases, kScanTiles at a time
+			const uint32_t b = b0 + threadIdx.x;
+			const uint32_t v = b < gridDim.x ? totals[b] : 0u;
+			uint32_t chunk_total;
+			const uint32_t excl = block_exclusive_scan(v, s_warp, chunk_total);
+			const uint32_t carry = s_carry;
+			if (b < gridDim.x) totals[b] = carry + excl;
 			__syncthreads();
-			s_part[threadIdx.x] += v;
+			if (threadIdx.x == 0) s_carry = carry + chunk_total;
 			__syncthreads();
 		}
-		uint32_t run = s_part[threadIdx.x] - sum;
-		for (uint32_t i = b; i < e; i++) {
-			out[i] = run;
-			const uint4 lo = *reinterpret_cast<const uint4*>(in + (size_t)i * 8), hi = *reinterpret_cast<const uint4*>(in + (size_t)i * 8 + 4);
-			run += __popc(lo.x) + __popc(lo.y) + __popc(lo.z) + __popc(lo.w) + __popc(hi.x) + __popc(hi.y) + __popc(hi.z) + __popc(hi.w);
-		}
-		const uint32_t total = s_part[blockDim.x - 1];
-		__syncthreads();
+		const uint32_t total = s_carry;
+		for (uint32_t t = kScanTiles + threadIdx.x; t < ntiles; t += kScanTiles) out[t] += totals[t / kScanTiles];  // (block 0's base is 0)
 		if (threadIdx.x == 0) {
 			out[ntiles] = total;
 			if (pass == 0) {
@@ -338,7 +379,7 @@ __global__ void __launch_bounds__(1024) scan_kernel(const FrameIO io, const uint
 		}
 		__syncthreads();
 	}
-	for (uint32_t i = threadIdx.x; i < ntiles * 2; i += blockDim.x) reinterpret_cast<uint4*>(clear_mask)[i] = make_uint4(0, 0, 0, 0);
+	if (threadIdx.x == 0) *ticket = 0;
 }
 
 // start of a bm_render / bm_launch_frame call: install the stop target; a target that is already met stops at once
@@ -568,6 +609,9 @@ struct bm_context {
 	bm_shadow* d_shadow = nullptr;  // RECORD scratch (sparse by slot)
 	uint32_t* d_shadow_mask = nullptr;
 	uint32_t* d_shadow_prefix = nullptr;
+	uint32_t* d_scan_totals = nullptr;  // scan_kernel: 2 * scan_blocks block totals
+	uint32_t* d_scan_ticket = nullptr;
+	uint32_t scan_blocks = 0;
 	bool private_valid = false;  // survivors of the last frame are in the private set DeviceState::cur (tile-local)
 	uint32_t caller_survivors = 0;  // primary_ray_cnt installed by bm_set_counters and not yet backed by records
 	// scene
@@ -707,6 +751,8 @@ void bm_destroy(bm_context* c) {
 	cudaFree(c->d_coarse);
 	cudaFree(c->d_fine);
 	cudaFree(c->d_flag);
+	cudaFree(c->d_scan_totals);
+	cudaFree(c->d_scan_ticket);
 	cudaFree(c->m_keys); cudaFree(c->m_vals); cudaFree(c->m_keys_sorted); cudaFree(c->m_vals_sorted); cudaFree(c->m_first); cudaFree(c->m_place); cudaFree(c->m_cub);
 	for (cudaEvent_t e : c->events) cudaEventDestroy(e);
 	if (c->stream) cudaStreamDestroy(c->stream);
@@ -759,6 +805,10 @@ int bm_create(bm_context** out, const bm_config* cfg) {
 	CKC(cudaMemset(c->d_shadow_mask, 0, (size_t)c->ntiles * 32));
 	CKC(cudaMalloc(&c->d_shadow_prefix, (size_t)(c->ntiles + 1) * 4));
 	CKC(cudaMalloc(&c->d_flag, 4));
+	c->scan_blocks = (c->ntiles + kScanTiles - 1) / kScanTiles;
+	CKC(cudaMalloc(&c->d_scan_totals, (size_t)c->scan_blocks * 8));
+	CKC(cudaMalloc(&c->d_scan_ticket, 4));
+	CKC(cudaMemset(c->d_scan_ticket, 0, 4));
 #undef CKC
 	// default camera (camera.h:4-9) and sun (variables.cpp:3)
 	const bm_camera def = { { 512, 512, 300 }, { 1, 0, 0 }, { 0, 0, 1 }, 1.f, 0.f };
@@ -1059,8 +1109,8 @@ static int launch_frame_kernels(bm_context* c, const FrameIO& io, bool count) {
 	if (c->timing) CK(cudaEventRecord(e1, c->stream));
 	// counts the survivors, advances the cursor, toggles DeviceState::cur; the mask that was this frame's input becomes the next
 	// frame's output: the scan clears it
-	scan_kernel<<<1, 1024, 0, c->stream>>>(io, RECORD ? io.shadow_mask : nullptr, RECORD ? c->d_shadow_prefix : nullptr, c->ntiles, c->cfg.ray_queue_buffer_size,
-	                                       c->tile_pixels);
+	scan_kernel<<<c->scan_blocks, kScanTiles, 0, c->stream>>>(io, RECORD ? io.shadow_mask : nullptr, RECORD ? c->d_shadow_prefix : nullptr, c->ntiles,
+	                                                          c->cfg.ray_queue_buffer_size, c->tile_pixels, c->d_scan_totals, c->d_scan_ticket);
 	CK(cudaGetLastError());
 	c->launches += 2;
 	return 0;
