@@ -263,8 +263,14 @@ __device__ __forceinline__ bool intersect_byte(const F3& origin, const F3& direc
 // profiles/r2_sass_loops.txt): the step's predicates stay live, so (1) the slice reload is two instructions predicated on "stepped
 // along z" instead of compare + branch + reconvergence, (2) the stepped axis is materialised once, at the hit, instead of two selects
 // per step, (3) the bit test is a 64-bit funnel shift + one predicate-setting AND.
+#ifndef BM_AABB_FAST
+#define BM_AABB_FAST 1
+#endif
+#ifndef BM_FINE64
+#define BM_FINE64 1
+#endif
 #ifndef BM_BRICK_PTX
-#define BM_BRICK_PTX 0
+#define BM_BRICK_PTX 1
 #endif
 __device__ __forceinline__ bool intersect_brick(const F3& origin, const F3& direction, const Dda& parent, F3& normal, float& distance, const bm_brick* brick) {
 	Dda a;
@@ -359,6 +365,15 @@ __device__ __forceinline__ bool intersect_brick(const F3& origin, const F3& dire
 
 // voxel.cuh:13-24
 __device__ __forceinline__ bool intersect_aabb(const SceneView& sv, const F3& o, const F3& d, float& tmin) {
+#if BM_AABB_FAST
+	// An origin strictly inside the box needs no arithmetic: per axis (0 - o) / d and (size - o) / d have opposite signs (or are
+	// -inf / +inf for d == 0), so every `lo` is negative and every `hi` positive whatever the rounding of the six divisions:
+	// tmin = max(0, lo...) = 0 and min(hi...) > 0. That is every bounce and shadow ray and every primary of an inside camera.
+	if (o.x > 0.f && o.x < sv.grid_size_f && o.y > 0.f && o.y < sv.grid_size_f && o.z > 0.f && o.z < sv.grid_height_f) {
+		tmin = 0.f;
+		return true;
+	}
+#endif
 	const F3 t1{ (0.0f - o.x) / d.x, (0.0f - o.y) / d.y, (0.0f - o.z) / d.z };
 	const F3 t2{ (sv.grid_size_f - o.x) / d.x, (sv.grid_size_f - o.y) / d.y, (sv.grid_height_f - o.z) / d.z };
 	const F3 lo{ gmin(t1.x, t2.x), gmin(t1.y, t2.y), gmin(t1.z, t2.z) };
@@ -459,7 +474,11 @@ __device__ __forceinline__ int trace_run(const SceneView& sv, const uint32_t* co
 			// is made only for cells that are non-empty or outside (with blocks of 4^3 cells the pair's index is the block bit's)
 			const int fbit = (a.pos.x & 3) | ((a.pos.y & 3) << 2) | ((a.pos.z & 3) << 4);
 			const uint32_t fidx = shift == 2 ? (uint32_t)((w << 5) + (bx & 31)) : (uint32_t)((a.pos.x >> 2) + (a.pos.y >> 2) * sv.fine_nx + (a.pos.z >> 2) * sv.fine_nxy);
+#if BM_FINE64
+			if ((__ldg(reinterpret_cast<const unsigned long long*>(sv.fine) + fidx) >> fbit) & 1ull) {  // one 64-bit load + funnel shift
+#else
 			if ((__ldg(sv.fine + (size_t)fidx * 2 + (fbit >> 5)) >> (fbit & 31)) & 1u) {
+#endif
 				const I3 p{ a.pos.x - bias, a.pos.y - bias, a.pos.z - bias };
 				if ((unsigned)p.x >= (unsigned)sv.cells || (unsigned)p.y >= (unsigned)sv.cells || (unsigned)p.z >= (unsigned)sv.cells_height) {  // voxel.cuh:256
 					if (COUNT) wc->steps--;  // not a cell test of the reference: its loop ended with the step that left the world
@@ -668,11 +687,18 @@ __device__ __forceinline__ Ray generate_primary(const FrameParams& fp, uint32_t 
 		  fmaf(nj, fp.cam_up.z, fmaf(ni, fp.cam_right.z, fp.cam_dir.z)) };
 	d = normalize_ref(d);
 	const F3 conv{ fmaf(fp.focal3, d.x, fp.cam_pos.x), fmaf(fp.focal3, d.y, fp.cam_pos.y), fmaf(fp.focal3, d.z, fp.cam_pos.z) };
-	const float l0 = random_float(seed);
-	const float l1 = random_float(seed);
-	float dx, dy;
-	concentric_disk(l0, l1, dx, dy);
-	const float plx = fp.lens_radius * dx, ply = fp.lens_radius * dy;
+	// Pinhole camera (lens radius 0, the reference's default, camera.h:9): the lens sample is multiplied by 0 (kernel.cu:195), so
+	// the disk map -- two draws, a division, a sine and a cosine -- need not be evaluated; 0 * finite = +-0 and position + (+-0) is
+	// the position for every non-zero position component (for a zero component the signed zero could differ: general path).
+	float plx = 0.f, ply = 0.f;
+	if (fp.lens_radius != 0.f || fp.cam_pos.x == 0.f || fp.cam_pos.y == 0.f || fp.cam_pos.z == 0.f) {
+		const float l0 = random_float(seed);
+		const float l1 = random_float(seed);
+		float dx, dy;
+		concentric_disk(l0, l1, dx, dy);
+		plx = fp.lens_radius * dx;
+		ply = fp.lens_radius * dy;
+	}
 	Ray r;
 	r.origin = F3{ fmaf(ply, fp.cam_up.x, fmaf(plx, fp.cam_right.x, fp.cam_pos.x)), fmaf(ply, fp.cam_up.y, fmaf(plx, fp.cam_right.y, fp.cam_pos.y)),
 		           fmaf(ply, fp.cam_up.z, fmaf(plx, fp.cam_right.z, fp.cam_pos.z)) };

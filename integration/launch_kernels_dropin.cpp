@@ -40,7 +40,12 @@ cudaError launch_kernels(State& state, cudaSurfaceObject_t surf, glm::vec4* blit
 		cfg.screen_height = (uint32_t)state.screen_height;
 		if ((rc = bm_create(&ctx, &cfg)) != 0) return rc > 0 ? (cudaError)rc : cudaErrorInvalidValue;
 	}
-	// GPUScene is passed by value every frame (launch.h:6); the pointer tables only change identity when the host re-creates them
+	// GPUScene is passed by value every frame (launch.h:6); the pointer tables only change identity when the host re-creates them.
+	// bm_scene_bind derives the emptiness bitmaps from the index words, so it is repeated only then. That is correct for the
+	// reference host: Scene.cpp never turns an empty cell into a non-empty one after generate() (streaming rewrites non-zero
+	// words only, Scene.cpp:158-164,224; growing a superchunk patches a brick-table ENTRY, Scene.cpp:242-246, which is read
+	// through the table every frame). A host that edits voxels in place (empty <-> non-empty cells) under the same table pointers
+	// must call bm_scene_bind itself after the edit.
 	if (bound.indices != gpuScene.indices || bound.bricks != gpuScene.bricks) {
 		bm_gpu_scene s;
 		memcpy(&s, &gpuScene, sizeof(s));
