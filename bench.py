@@ -144,11 +144,26 @@ def views_for(conf):
     return [((512.0, 512.0, 300.0), (1.0, 0.0, 0.0))]
 
 
-def caves_camera(grid, k):
-    """Camera of step k in the cave world: a walk along the view direction from the centre, 96 voxels (12 cells) per step."""
+def caves_camera(grid, k, indices_of=None):
+    """Camera of step k in the cave world: a walk along the view direction from the centre, 96 voxels (12 cells) per step, snapped to
+    open space. indices_of(superchunk) -> the 4096 host-view index words of that superchunk (0 = empty cell): the camera is put at the
+    centre of the nearest empty cell whose six neighbours are empty too -- a camera inside rock renders nothing (every primary hits at
+    distance 0 and bounces off a zero normal into a NaN ray, like in the reference)."""
+    import numpy as np
     c = grid / 2
     d = (0.8017837, 0.5345225, 0.2672612)
-    return (c + 37.0 + 96.0 * k * d[0], c - 91.0 + 96.0 * k * d[1], c + 13.0 + 96.0 * k * d[2]), d
+    p = np.array([c + 37.0 + 96.0 * k * d[0], c - 91.0 + 96.0 * k * d[1], c + 13.0 + 96.0 * k * d[2]])
+    if indices_of is not None:
+        sg = grid // 128
+        s3 = (p // 128).astype(int)
+        idx = np.asarray(indices_of(int(s3[0] + sg * (s3[1] + sg * s3[2])))).reshape(16, 16, 16)  # [z][y][x]
+        occ = np.pad(idx != 0, 1, constant_values=True)
+        ok = ~(occ[1:-1, 1:-1, 1:-1] | occ[:-2, 1:-1, 1:-1] | occ[2:, 1:-1, 1:-1] | occ[1:-1, :-2, 1:-1] | occ[1:-1, 2:, 1:-1] | occ[1:-1, 1:-1, :-2] | occ[1:-1, 1:-1, 2:])
+        if ok.any():
+            z, y, x = np.nonzero(ok)
+            centres = np.stack([x, y, z], 1) * 8.0 + 4.37 + s3 * 128.0
+            p = centres[np.argmin(((centres - p) ** 2).sum(1))]
+    return (float(p[0]), float(p[1]), float(p[2])), d
 
 
 # ---------------------------------------------------------------------------------------------------------------------
@@ -164,7 +179,7 @@ def cpu_baseline_port(conf, frames=3):
         # the oracle cannot generate 2^39 voxels in bounded time: the same generator at 1024^3 (1/512 of the volume), all resident
         grid = 1024
         scene = ob.OracleScene(orc, grid, grid).generate_caves(seed=1).set_residency(True)
-        pos, d = caves_camera(grid, 0)
+        pos, d = caves_camera(grid, 0, scene.host_indices)
         cam = ob.make_camera(position=pos, direction=d)
         what = "the same cave generator at 1024^3 voxels (1/512 of the volume), all bricks resident, first %d frames" % frames
     else:
@@ -387,6 +402,15 @@ def main():
     scratch = torch.zeros(64 * 1024 * 1024, dtype=torch.float32, device=dev)
     views = views_for(conf)
     state = {"k": 0, "frames": 4000, "stream_frames": 0}
+    cave_path = {}
+
+    def cave_view(k):  # (memoised: reading index words back synchronises the device; the path is laid out before anything is timed)
+        if k not in cave_path:
+            cave_path[k] = caves_camera(conf["grid"], k, lambda sc: store.indices(sc, host_view=True))
+        return cave_path[k]
+    if caves:
+        for k in range(2 + 1 + args.warmup + 2 * args.steps + 1):
+            cave_view(k)
 
     def render_view(flags):
         """reset (the caller moved camera or sun) and render to the path target"""
@@ -410,7 +434,7 @@ def main():
                 ren.synchronize()
             return
         if caves:
-            todo = [caves_camera(conf["grid"], state["k"])]  # a camera move resets the accumulation (kernel.cu:387-403)
+            todo = [cave_view(state["k"])]  # a camera move resets the accumulation (kernel.cu:387-403)
             state["k"] += 1
         else:
             todo = views
@@ -428,7 +452,7 @@ def main():
         for probe_step in range(1 if not caves else 2):
             if caves:
                 state["k"] += 1
-            for pos, d in (views or [caves_camera(conf["grid"], state["k"] - 1)]):
+            for pos, d in (views or [cave_view(state["k"] - 1)]):
                 ren.set_camera(bm.make_camera(position=pos, direction=d))
                 ren.set_sun(*SUN)
                 ren.reset_stats()
@@ -559,7 +583,8 @@ def main():
               "l2": "flushed between steps (256 MiB write); scene %s > L2" % ("593 MiB" if not caves else "8 GiB of index words")}
     if caves:
         config.update(scene_generation_s=t_gen, bricks_total=store.total_bricks, requests_in_queue_after_last_step=requests_left, queue_size=cfg.brick_load_queue_size,
-                      requests_per_step_counting_pass=work["requests"], camera_steps_taken=state["k"])
+                      requests_per_step_counting_pass=work["requests"], camera_steps_taken=state["k"],
+                      camera_path=[[round(v, 2) for v in cave_path[k][0]] for k in sorted(cave_path)][: state["k"]])
     out = {"metric": conf["metric"], "value": value, "unit": "Mrays/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_max / args.steps,
            "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": config,
            "clocks": clocks, "e2e": {"value": e2e_value, "unit": "Mrays/s", "h2d_bytes_per_step": (C.sizeof(bm.Camera) + 8 + 8) * nviews,

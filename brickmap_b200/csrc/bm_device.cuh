@@ -32,6 +32,21 @@ __device__ __forceinline__ F3 make_f3(float x, float y, float z) { return F3{ x,
 __device__ __forceinline__ float comp(const F3& v, int i) { return i == 0 ? v.x : (i == 1 ? v.y : v.z); }
 __device__ __forceinline__ int comp(const I3& v, int i) { return i == 0 ? v.x : (i == 1 ? v.y : v.z); }
 
+// v[i] for i in {0, 1, 2} as two selects
+__device__ __forceinline__ float sel3(const F3& v, int i) {
+	float r;
+	asm("{\n\t"
+	    ".reg .pred p0, p1;\n\t"
+	    "setp.eq.s32 p0, %4, 0;\n\t"
+	    "setp.eq.s32 p1, %4, 1;\n\t"
+	    "selp.f32 %0, %2, %3, p1;\n\t"
+	    "selp.f32 %0, %1, %0, p0;\n\t"
+	    "}"
+	    : "=f"(r)
+	    : "f"(v.x), "f"(v.y), "f"(v.z), "r"(i));
+	return r;
+}
+
 // GLM's scalar min/max/sign (documented semantics; NaN behaviour follows from the comparisons)
 __device__ __forceinline__ float gmin(float x, float y) { return (y < x) ? y : x; }
 __device__ __forceinline__ float gmax(float x, float y) { return (x < y) ? y : x; }
@@ -235,6 +250,21 @@ __device__ __forceinline__ F3 axis_normal(const Dda& a, int axis) {  // normal[s
 	return F3{ axis == 0 ? -(float)a.stepi.x : 0.f, axis == 1 ? -(float)a.stepi.y : 0.f, axis == 2 ? -(float)a.stepi.z : 0.f };
 }
 
+// bit n (0..63) of a 64-bit mask as a 32-bit value: one funnel shift + one AND (the compiler's own form compares 64 bits)
+__device__ __forceinline__ uint32_t bit64(unsigned long long mask, int n) {
+	uint32_t r;
+	asm("{\n\t"
+	    ".reg .b64 t;\n\t"
+	    ".reg .b32 w;\n\t"
+	    "shr.u64 t, %1, %2;\n\t"
+	    "cvt.u32.u64 w, t;\n\t"
+	    "and.b32 %0, w, 1;\n\t"
+	    "}"
+	    : "=r"(r)
+	    : "l"(mask), "r"(n));
+	return r;
+}
+
 // voxel.cuh:26-77 (2x2x2 LoD octants)
 __device__ __forceinline__ bool intersect_byte(const F3& origin, const F3& direction, const Dda& parent, F3& normal, float& distance, uint32_t byte) {
 	Dda a;
@@ -283,7 +313,7 @@ __device__ __forceinline__ bool intersect_brick(const F3& origin, const F3& dire
 	const uint2* slices = reinterpret_cast<const uint2*>(brick->data);  // bricks are 64-byte aligned (Scene.cpp:170-176)
 #if BM_BRICK_PTX
 	const unsigned long long first = __ldg(reinterpret_cast<const unsigned long long*>(slices) + a.pos.z);
-	if ((first >> (a.pos.x + a.pos.y * 8)) & 1ull) return true;  // the ray starts in a solid voxel: normal and distance stay (voxel.cuh:114-119)
+	if (bit64(first, a.pos.x + a.pos.y * 8)) return true;  // the ray starts in a solid voxel: normal and distance stay (voxel.cuh:114-119)
 	uint32_t hit;
 	asm volatile(
 	    "{\n\t"
@@ -303,8 +333,7 @@ __device__ __forceinline__ bool intersect_brick(const F3& origin, const F3& dire
 	    "@mx add.rn.f32 %3, %3, %12;\n\t"
 	    "@my add.rn.f32 %4, %4, %13;\n\t"
 	    "@mz add.rn.f32 %5, %5, %14;\n\t"
-	    "or.b32 any, %0, %1;\n\t"                        // left the brick: some coordinate is -1 or 8 (voxel.cuh:128)
-	    "or.b32 any, any, %2;\n\t"
+	    "lop3.b32 any, %0, %1, %2, 0xfe;\n\t"            // x | y | z: left the brick when some coordinate is -1 or 8 (voxel.cuh:128)
 	    "setp.gt.u32 pout, any, 7;\n\t"
 	    "@pout bra BM_BRICK_MISS;\n\t"
 	    "@!mz bra BM_BRICK_SAME_SLICE;\n\t"              // (ptxas turns a predicated load into a branch anyway; this way the address
@@ -369,7 +398,10 @@ __device__ __forceinline__ bool intersect_aabb(const SceneView& sv, const F3& o,
 	// An origin strictly inside the box needs no arithmetic: per axis (0 - o) / d and (size - o) / d have opposite signs (or are
 	// -inf / +inf for d == 0), so every `lo` is negative and every `hi` positive whatever the rounding of the six divisions:
 	// tmin = max(0, lo...) = 0 and min(hi...) > 0. That is every bounce and shadow ray and every primary of an inside camera.
-	if (o.x > 0.f && o.x < sv.grid_size_f && o.y > 0.f && o.y < sv.grid_size_f && o.z > 0.f && o.z < sv.grid_height_f) {
+	// Only for a FINITE direction: a NaN component (the bounce off a vertex whose normal is still 0, i.e. a camera inside a solid voxel)
+	// makes the reference's comparisons false and the ray miss (voxel.cuh:23) -- and would make the DDA below spin on NaN tmax.
+	if (o.x > 0.f && o.x < sv.grid_size_f && o.y > 0.f && o.y < sv.grid_size_f && o.z > 0.f && o.z < sv.grid_height_f &&
+	    fabsf(d.x + d.y + d.z) <= 3.0e38f) {
 		tmin = 0.f;
 		return true;
 	}
@@ -475,7 +507,7 @@ __device__ __forceinline__ int trace_run(const SceneView& sv, const uint32_t* co
 			const int fbit = (a.pos.x & 3) | ((a.pos.y & 3) << 2) | ((a.pos.z & 3) << 4);
 			const uint32_t fidx = shift == 2 ? (uint32_t)((w << 5) + (bx & 31)) : (uint32_t)((a.pos.x >> 2) + (a.pos.y >> 2) * sv.fine_nx + (a.pos.z >> 2) * sv.fine_nxy);
 #if BM_FINE64
-			if ((__ldg(reinterpret_cast<const unsigned long long*>(sv.fine) + fidx) >> fbit) & 1ull) {  // one 64-bit load + funnel shift
+			if (bit64(__ldg(reinterpret_cast<const unsigned long long*>(sv.fine) + fidx), fbit)) {  // one 64-bit load + funnel shift
 #else
 			if ((__ldg(sv.fine + (size_t)fidx * 2 + (fbit >> 5)) >> (fbit & 31)) & 1u) {
 #endif
@@ -494,10 +526,13 @@ __device__ __forceinline__ int trace_run(const SceneView& sv, const uint32_t* co
 				const uint32_t index = __ldg(word);
 				if (COUNT) wc->index_reads++;
 				if (index) {
-					float new_distance = 0.f;
-					if (step_axis != -1) {
-						normal = axis_normal(a, step_axis);
-						new_distance = comp(a.tmax, step_axis) - comp(a.tdelta, step_axis);
+					// voxel.cuh:201-206, branch-free: component `step_axis` of tmax and tdelta through selects (the compiler's form is a
+					// tree of branches), nothing changes when no step has been taken yet (step_axis == -1)
+					const bool stepped = step_axis != -1;
+					const float new_distance = stepped ? sel3(a.tmax, step_axis) - sel3(a.tdelta, step_axis) : 0.f;
+					{
+						const F3 n = axis_normal(a, step_axis);
+						normal = F3{ stepped ? n.x : normal.x, stepped ? n.y : normal.y, stepped ? n.z : normal.z };
 					}
 					const int dx = cam.x - p.x, dy = cam.y - p.y, dz = cam.z - p.z;
 					const int lod_distance_squared = dx * dx + dy * dy + dz * dz;

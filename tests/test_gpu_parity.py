@@ -878,6 +878,36 @@ def _oracle_scene_4096(oracle):
     return _ORACLE_4096[0]
 
 
+def test_camera_inside_a_solid_voxel_terminates_like_the_reference(oracle, golden, stores):
+    """A camera inside rock: every primary hits at distance 0 with the normal still (0,0,0) (voxel.cuh:114-119), the bounce off a
+    zero normal is a NaN direction (kernel.cu:76-84,293), and the reference's AABB test then rejects the NaN ray (all comparisons
+    false, voxel.cuh:23): the path ends as a miss with NaN radiance. The product must do the same -- in particular a NaN ray must
+    never reach the DDA, which would spin on NaN tmax. NaNs are compared as NaNs (their payload bits differ between CPU and GPU)."""
+    g = golden("256")
+    w, h, n = 128, 96, 16384
+    cfg = cfg_from_golden(g)
+    cfg.screen_width, cfg.screen_height, cfg.ray_queue_buffer_size = w, h, n
+    store = stores("256")
+    pos = (100.5, 90.25, 20.75)
+    ren = bm.Renderer(cfg, store)
+    ren.set_camera(bm.make_camera(position=pos, direction=g["cam_dir"]))
+    s = ob.OracleScene(oracle, 256, 256).generate_terrain().set_residency(True)
+    oren = ob.OracleRenderer(s, w, h, n, ob.make_camera(position=pos, direction=g["cam_dir"]))
+    blit = torch.zeros(h, w, 4, dtype=torch.float32, device="cuda")
+    for f in range(4):
+        ren.render(blit, 1)
+        oren.frame()
+        c = ren.counters()
+        assert [c.primary_ray_cnt, c.start_position, c.frame] == [oren.state.primary_ray_cnt, oren.state.start_position, oren.state.frame]
+        mine, want = ren.export_rays(), oren.rays[: c.primary_ray_cnt]
+        for fld in ("origin", "direction", "normal"):
+            a, b = mine[fld], want[fld]
+            assert np.array_equal(np.isnan(a), np.isnan(b)) and np.array_equal(bits(a)[~np.isnan(a)], bits(b)[~np.isnan(b)]), "frame %d field %s" % (f + 1, fld)
+    assert oren.state.frame == 5 and np.isnan(oren.accum).any(), "the scenario must produce NaN rays"
+    acc = blit.cpu().numpy()
+    assert np.array_equal(np.isnan(acc), np.isnan(oren.accum)) and np.array_equal(acc[..., 3], oren.accum[..., 3])
+
+
 # ---- against the live reference -------------------------------------------------------------------------------------
 @pytest.mark.skipif(not ob.Reference.available("256"), reason="oracle/_ref not built")
 def test_drop_in_on_the_reference_hosts_own_scene(golden):
