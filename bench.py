@@ -509,6 +509,22 @@ def main():
     rays = stats["extend_rays"] + stats["shadow_rays"]
     requests_left = ren.load_queue()[0] if caves else 0
 
+    per_view = None
+    if conf.get("tour"):  # one more pass, view by view (device time per view; same work as inside a step)
+        per_view = []
+        for pos, d in views:
+            ren.set_camera(bm.make_camera(position=pos, direction=d))
+            ren.set_sun(*SUN)
+            ren.reset_stats()
+            torch.cuda.synchronize(dev)
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record(stream)
+            render_view(0)
+            e1.record(stream)
+            e1.synchronize()
+            vs = ren.stats()
+            per_view.append(round((vs["extend_rays"] + vs["shadow_rays"]) / (e0.elapsed_time(e1) * 1e-3) / 1e6, 1))
+
     # ---- e2e: the public call with HOST buffers (pinned): camera/sun in, accumulation tile + request buffer out
     if world > 1:
         dist.barrier()
@@ -581,6 +597,8 @@ def main():
               "paths": "whole frames until the target (overshoot)" if args.overshoot else "exactly spp paths per pixel (BM_FRAME_EXACT_PATHS)",
               "partition": "whole image" if world == 1 else "%d ranks, interleaved strips of %d rows (%d rows on rank 0)" % (world, STRIP, rows),
               "l2": "flushed between steps (256 MiB write); scene %s > L2" % ("593 MiB" if not caves else "8 GiB of index words")}
+    if per_view is not None:
+        config["per_view_mrays"] = per_view  # (rank 0's share of each view)
     if caves:
         config.update(scene_generation_s=t_gen, bricks_total=store.total_bricks, requests_in_queue_after_last_step=requests_left, queue_size=cfg.brick_load_queue_size,
                       requests_per_step_counting_pass=work["requests"], camera_steps_taken=state["k"],

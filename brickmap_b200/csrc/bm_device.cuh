@@ -469,7 +469,7 @@ constexpr int kTraceChunk = BM_TRACE_CHUNK;  // cell tests between two looks at 
 // per slab) as compile-time constants.
 template <bool COUNT, bool BOUNDED, bool STOCK = false>
 __device__ __forceinline__ int trace_run(const SceneView& sv, const uint32_t* coarse_smem, const F3 direction, F3& normal, float& distance, const I3 cam,
-                                         TraceState& ts, int budget, WorkCounters* wc, int min_lanes = 0, int inline_tests = 0x7FFFFFFF) {
+                                         TraceState& ts, int budget, WorkCounters* wc, int min_lanes = 0) {
 	const F3 origin = ts.origin;
 	const float tminn = ts.tminn;
 	Dda& a = ts.a;
@@ -548,11 +548,6 @@ __device__ __forceinline__ int trace_run(const SceneView& sv, const uint32_t* co
 								return TRACE_HIT;
 						}
 					} else if (index & BM_BRICK_LOADED_BIT) {  // voxel.cuh:222-227
-						// BOUNDED: a brick met later than the first `inline_tests` cell tests of this call is not walked now, with the
-						// few lanes that happen to be at a brick in this very iteration: the ray is suspended IN FRONT of the cell. Resumed,
-						// it tests the cell again first thing, next to the other rays of its batch that were suspended the same way, and
-						// they walk their bricks together. (normal was set above; the resumed test sets it again.)
-						if (BOUNDED && (budget - it) + (kTraceChunk - chunk) >= inline_tests) return TRACE_SUSPENDED;
 						const bm_brick* b = bricks_sc + (index & BM_BRICK_INDEX_BITS);
 						// both 32-byte halves of the brick on their way while the sub-DDA is set up (its loads are one word per step)
 						asm volatile("prefetch.global.L1 [%0];" ::"l"(b));

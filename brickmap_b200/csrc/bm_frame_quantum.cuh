@@ -49,7 +49,6 @@ struct QSched {
 	int quantum;       // cell tests a ray may take in one batch before it is suspended
 	int min_share;     // a batch is given up once fewer than min_share / 32 of the lanes that started tracing are left
 	int descending;    // hand out slot runs from the end of the frame
-	int inline_tests;  // bricks met after this many cell tests of a batch suspend the ray in front of the brick
 	int run_len;       // a warp pulls run_len * 32 consecutive slots per ticket
 	int resume_at;     // queued rays are resumed as soon as this many have piled up (<= 32)
 };
@@ -91,7 +90,7 @@ __device__ __forceinline__ void stage_bitmap(uint32_t* s_coarse, const uint32_t*
 // RECORD (bm_launch_frame): additionally leaves the post-extend record of every slot and the shadow-ray records, like frame_kernel<RECORD>
 template <bool STOCK, bool RECORD>
 __global__ void __launch_bounds__(kQBlock, 1) frame_kernel_q(const FrameParams fp, const SceneView sv, const FrameIO io, const QSched sch) {
-	const int quantum = sch.quantum, min_share = sch.min_share, descending = sch.descending, inline_tests = sch.inline_tests;
+	const int quantum = sch.quantum, min_share = sch.min_share, descending = sch.descending;
 	extern __shared__ __align__(16) uint32_t s_coarse[];
 	DeviceState* st = io.st;
 	if (st->done) return;
@@ -204,7 +203,7 @@ __global__ void __launch_bounds__(kQBlock, 1) frame_kernel_q(const FrameParams f
 			// no suspending where it cannot regroup anything: rays that entered from outside (see above), and the last batch of a
 			// warp whose queue and slot pool are both empty
 			const bool pinned = ts.tminn > 0.f || (pool_dry && qn == 0);
-			status = trace_run<false, true, STOCK>(sv, coarse, direction, normal, distance, fp.cam_cell, ts, pinned ? 0x3FFFFFF8 : quantum, &wc, pinned ? 0 : min_lanes, pinned ? 0x7FFFFFFF : inline_tests);
+			status = trace_run<false, true, STOCK>(sv, coarse, direction, normal, distance, fp.cam_cell, ts, pinned ? 0x3FFFFFF8 : quantum, &wc, pinned ? 0 : min_lanes);
 		}
 		__syncwarp();  // lanes whose ray ended early wait here: they are shaded together, not interleaved with the tracing lanes
 

@@ -283,7 +283,7 @@ def test_throughput_kernel_matches_simple_kernel_on_the_stock_world(golden, stor
 @pytest.mark.parametrize("variant", ["256lod", "4096"])
 def test_throughput_kernel_schedules_agree(golden, stores, variant, monkeypatch):
     """How long a batch runs before its unfinished rays are suspended (fixed quantum; given up early when the warp thins out;
-    suspended in front of bricks), in which order slot runs are handed out and whether the stock world's bitmap geometry is
+    ), in which order slot runs are handed out and whether the stock world's bitmap geometry is
     compiled in are schedules / code paths of the same arithmetic:
     survivors bit for bit, alpha exactly, radiance to 1e-5 (the order of the float atomics differs)."""
     g = golden(variant)
@@ -291,15 +291,13 @@ def test_throughput_kernel_schedules_agree(golden, stores, variant, monkeypatch)
     cfg = store.cfg
     h, w = cfg.screen_height, cfg.screen_width
     results = []
-    for quantum, share, no_stock, inline, descending, run_len, resume_at in (
-            (64, 0, 0, 0, 0, 1, 32), (16, 0, 0, 0, 0, 4, 32), (256, 16, 0, 0, 0, 1, 32), (512, 28, 0, 0, 1, 2, 24), (256, 16, 1, 0, 0, 1, 32),
-            (256, 16, 0, 1, 0, 1, 32), (128, 8, 0, 3, 1, 16, 7)):
+    for quantum, share, no_stock, descending, run_len, resume_at in (
+            (64, 0, 0, 0, 1, 32), (16, 0, 0, 0, 4, 32), (256, 16, 0, 0, 1, 32), (512, 28, 0, 1, 2, 24), (256, 16, 1, 0, 1, 32), (128, 8, 0, 1, 16, 7)):
         monkeypatch.setenv("BRICKMAP_B200_RUN_LEN", str(run_len))
         monkeypatch.setenv("BRICKMAP_B200_RESUME_AT", str(resume_at))
         monkeypatch.setenv("BRICKMAP_B200_QUANTUM", str(quantum))
         monkeypatch.setenv("BRICKMAP_B200_MIN_SHARE", str(share))
         monkeypatch.setenv("BRICKMAP_B200_NO_STOCK", str(no_stock))
-        monkeypatch.setenv("BRICKMAP_B200_INLINE_TESTS", str(inline))  # 0 = default: bricks are always walked where they are met
         monkeypatch.setenv("BRICKMAP_B200_DESCENDING", str(descending))
         ren = renderer_for(g, store)  # the switches are read when the scene is bound
         blit = torch.zeros(h, w, 4, dtype=torch.float32, device="cuda")
