@@ -452,7 +452,7 @@ __device__ __forceinline__ bool trace_setup(const SceneView& sv, F3 origin, cons
 	return true;
 }
 
-enum : int { TRACE_MISS = 0, TRACE_HIT = 1, TRACE_SUSPENDED = 2 };
+enum : int { TRACE_MISS = 0, TRACE_HIT = 1, TRACE_SUSPENDED = 2, TRACE_AT_BRICK = 3 };  // AT_BRICK: suspended in front of a cell whose brick is to be walked
 #ifndef BM_TRACE_CHUNK
 #define BM_TRACE_CHUNK 16
 #endif
@@ -469,7 +469,7 @@ constexpr int kTraceChunk = BM_TRACE_CHUNK;  // cell tests between two looks at 
 // per slab) as compile-time constants.
 template <bool COUNT, bool BOUNDED, bool STOCK = false>
 __device__ __forceinline__ int trace_run(const SceneView& sv, const uint32_t* coarse_smem, const F3 direction, F3& normal, float& distance, const I3 cam,
-                                         TraceState& ts, int budget, WorkCounters* wc, int min_lanes = 0) {
+                                         TraceState& ts, int budget, WorkCounters* wc, int min_lanes = 0, int brick_lanes = 0) {
 	const F3 origin = ts.origin;
 	const float tminn = ts.tminn;
 	Dda& a = ts.a;
@@ -548,6 +548,12 @@ __device__ __forceinline__ int trace_run(const SceneView& sv, const uint32_t* co
 								return TRACE_HIT;
 						}
 					} else if (index & BM_BRICK_LOADED_BIT) {  // voxel.cuh:222-227
+						// BOUNDED: a brick that only a few lanes of the warp have reached in this very iteration is not walked now -- that would
+						// cost the whole warp a brick set-up and walk (~300 instructions) for two or three rays. The ray is suspended IN FRONT of
+						// the cell instead (exact: the state is untouched); resumed, it tests this cell first thing, next to the other rays of its
+						// batch that were suspended the same way, and they walk their bricks together. Never at the first test of a call (a
+						// resumed ray must make progress), never where many lanes arrive together (coherent rays: nothing to gain).
+						if (BOUNDED && brick_lanes && (it != budget || chunk != kTraceChunk) && __popc(__activemask()) < brick_lanes) return TRACE_AT_BRICK;
 						const bm_brick* b = bricks_sc + (index & BM_BRICK_INDEX_BITS);
 						// both 32-byte halves of the brick on their way while the sub-DDA is set up (its loads are one word per step)
 						asm volatile("prefetch.global.L1 [%0];" ::"l"(b));

@@ -51,6 +51,7 @@ struct QSched {
 	int descending;    // hand out slot runs from the end of the frame
 	int run_len;       // a warp pulls run_len * 32 consecutive slots per ticket
 	int resume_at;     // queued rays are resumed as soon as this many have piled up (<= 32)
+	int brick_lanes;   // a brick reached by fewer lanes than this (in the same iteration) suspends the ray in front of it (0: never)
 };
 
 // The block's copy of the emptiness bitmap (46 KiB at reference dims). BM_BULK_PROLOGUE=1: ONE bulk asynchronous copy global -> shared
@@ -203,7 +204,7 @@ __global__ void __launch_bounds__(kQBlock, 1) frame_kernel_q(const FrameParams f
 			// no suspending where it cannot regroup anything: rays that entered from outside (see above), and the last batch of a
 			// warp whose queue and slot pool are both empty
 			const bool pinned = ts.tminn > 0.f || (pool_dry && qn == 0);
-			status = trace_run<false, true, STOCK>(sv, coarse, direction, normal, distance, fp.cam_cell, ts, pinned ? 0x3FFFFFF8 : quantum, &wc, pinned ? 0 : min_lanes);
+			status = trace_run<false, true, STOCK>(sv, coarse, direction, normal, distance, fp.cam_cell, ts, pinned ? 0x3FFFFFF8 : quantum, &wc, pinned ? 0 : min_lanes, pinned ? 0 : sch.brick_lanes);
 		}
 		__syncwarp();  // lanes whose ray ended early wait here: they are shaded together, not interleaved with the tracing lanes
 
@@ -211,7 +212,7 @@ __global__ void __launch_bounds__(kQBlock, 1) frame_kernel_q(const FrameParams f
 		int push = K_NONE;  // what this lane appends to the queue
 		F3 push_o{ 0.f, 0.f, 0.f }, push_d{ 0.f, 0.f, 0.f }, push_c{ 0.f, 0.f, 0.f };
 		if (kind != K_NONE) {
-			if (status == TRACE_SUSPENDED) {
+			if (status == TRACE_SUSPENDED || status == TRACE_AT_BRICK) {
 				push = kind;
 			} else if (kind == K_SHADOW) {
 				if (status == TRACE_MISS) {  // kernel.cu:340-344

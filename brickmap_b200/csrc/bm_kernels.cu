@@ -643,6 +643,7 @@ struct bm_context {
 	int min_share = 18;       // BRICKMAP_B200_MIN_SHARE: a batch is given up when fewer than min_share / 32 of its tracing lanes are left (16: 3095, 18-20 with resume_at 24: 3110 Mrays/s)
 	int run_len = 1;          // BRICKMAP_B200_RUN_LEN (1: 2723, 2: 2666, 4: 2503, 8: 2215, 16: 1683 Mrays/s -- the runs a warp still holds when the pool runs dry are the frame's tail)
 	int resume_at = 24;       // BRICKMAP_B200_RESUME_AT (profiles/r2_j_sweep_resume_at.txt)
+	int brick_lanes = 3;      // BRICKMAP_B200_BRICK_LANES (0: 3089, 2: 3184, 3: 3200, 4: 3192, 6: 3157, 10: 3031, 16: 2886 Mrays/s): bricks reached by fewer lanes than this suspend the ray in front of the brick (0: never)
 	int descending = 0;       // BRICKMAP_B200_DESCENDING: hand out slot runs from the end of the frame
 	// scratch of bm_requests_merge (sized for world * queue entries on first use)
 	uint32_t *m_keys = nullptr, *m_vals = nullptr, *m_keys_sorted = nullptr, *m_vals_sorted = nullptr, *m_first = nullptr, *m_place = nullptr;
@@ -905,6 +906,7 @@ int bm_scene_bind(bm_context* c, bm_gpu_scene scene) {
 	c->quantum = (c->quantum + kTraceChunk - 1) / kTraceChunk * kTraceChunk;
 	if (const char* e = getenv("BRICKMAP_B200_RUN_LEN")) c->run_len = atoi(e) >= 1 && atoi(e) <= 64 ? atoi(e) : c->run_len;
 	if (const char* e = getenv("BRICKMAP_B200_RESUME_AT")) c->resume_at = atoi(e) >= 1 && atoi(e) <= 32 ? atoi(e) : c->resume_at;
+	if (const char* e = getenv("BRICKMAP_B200_BRICK_LANES")) c->brick_lanes = atoi(e) >= 0 && atoi(e) <= 32 ? atoi(e) : c->brick_lanes;
 	if (const char* e = getenv("BRICKMAP_B200_DESCENDING")) c->descending = e[0] == '1';
 	if (const char* e = getenv("BRICKMAP_B200_MIN_SHARE")) c->min_share = atoi(e) >= 0 && atoi(e) <= 32 ? atoi(e) : c->min_share;
 	if (sv.cells + (2 << shift) > 65535 || sv.cells_height + (2 << shift) > 4095) c->use_quantum = false;  // queue entries pack the biased cell position into 16 + 16 + 12 bits
@@ -1098,7 +1100,7 @@ static int launch_frame_kernels(bm_context* c, const FrameIO& io, bool count) {
 	else if (!c->use_quantum) frame_kernel<RECORD, false><<<blocks, kTile, c->frame_smem, c->stream>>>(c->fp, c->sv, io);
 	else {
 		const size_t smem = RECORD ? c->q_smem_record : c->q_smem;
-		const QSched sch{ c->quantum, c->min_share, c->descending, c->run_len, c->resume_at };
+		const QSched sch{ c->quantum, c->min_share, c->descending, c->run_len, c->resume_at, c->brick_lanes };
 		if (RECORD) CK(cudaMemsetAsync(io.shadow_mask, 0, (size_t)c->ntiles * 32, c->stream));  // the kernel sets bits with atomicOr
 		if (c->q_stock) frame_kernel_q<true, RECORD><<<c->q_blocks, kQBlock, smem, c->stream>>>(c->fp, c->sv, io, sch);
 		else frame_kernel_q<false, RECORD><<<c->q_blocks, kQBlock, smem, c->stream>>>(c->fp, c->sv, io, sch);
