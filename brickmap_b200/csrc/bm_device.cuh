@@ -454,9 +454,9 @@ __device__ __forceinline__ bool trace_setup(const SceneView& sv, F3 origin, cons
 
 enum : int { TRACE_MISS = 0, TRACE_HIT = 1, TRACE_SUSPENDED = 2, TRACE_AT_BRICK = 3 };  // AT_BRICK: suspended in front of a cell whose brick is to be walked
 #ifndef BM_TRACE_CHUNK
-#define BM_TRACE_CHUNK 16
+#define BM_TRACE_CHUNK 32
 #endif
-constexpr int kTraceChunk = BM_TRACE_CHUNK;  // cell tests between two looks at the budget (8: 2509, 16: 2530 Mrays/s)
+constexpr int kTraceChunk = BM_TRACE_CHUNK;  // cell tests between two looks at the budget (8: 3154, 16: 3192, 32: 3207 Mrays/s, profiles/r2_n_ab_chunk_quantum.txt)
 
 // The DDA loop of intersect_voxel (voxel.cuh:192-259). `coarse_smem` is the block's shared-memory copy of the emptiness
 // bitmap. The DDA performs exactly the reference's sequence of floating-point steps; only the LOADS of index words for empty
