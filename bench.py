@@ -576,9 +576,10 @@ def main():
         from brickmap_b200.build import source_hash
         with open(os.path.join(ROOT, "profiles", "frame_kernel_traffic.json")) as f:
             tj = json.load(f)
-        if tj.get("source_hash") == source_hash() and tj.get("config") == args.config and world == 1:
-            traffic, traffic_note = tj.get("dram_bytes_per_launch"), "ncu --set full capture of one launch of these kernel sources (hash %s)" % tj["source_hash"]
-        elif tj.get("config") == args.config and world == 1:
+        entry = (tj.get("configs") or {}).get(args.config)
+        if entry and tj.get("source_hash") == source_hash() and world == 1:
+            traffic, traffic_note = entry.get("dram_bytes_per_launch"), "ncu --set full capture of one launch of these kernel sources (hash %s), %s" % (tj["source_hash"], entry.get("report"))
+        elif entry and world == 1:
             traffic_note = "the committed capture describes kernel sources %s, this tree is %s" % (tj.get("source_hash"), source_hash())
     except Exception:
         pass

@@ -91,6 +91,12 @@ __device__ __forceinline__ void accum_add(float4* accum, uint32_t pixel, float r
 
 // Where is survivor number `k` of the previous frame? Stable compaction = the reference's atomicAdd(&primary_ray_cnt, 1)
 // (kernel.cu:298-299) with the schedule fixed to slot order; the records themselves are never moved.
+// Prefix layout of a survivor set (two levels, so that the scan needs no pass over all tiles to add block bases): prefix[t], t < ntiles =
+// survivors of the tiles before t INSIDE t's scan block (kScanTiles tiles); prefix[ntiles] = total; prefix[ntiles + 1 + b] = survivors
+// before scan block b (b <= nblocks; the last entry is the total again).
+constexpr int kScanTiles = 256;
+__host__ __device__ __forceinline__ uint32_t scan_block_count(uint32_t ntiles) { return (ntiles + kScanTiles - 1) / kScanTiles; }
+__host__ __device__ __forceinline__ size_t prefix_words(uint32_t ntiles) { return (size_t)ntiles + 2 + scan_block_count(ntiles); }
 struct SurvivorSet {
 	const bm_ray* in;
 	const uint32_t* in_mask;
@@ -107,12 +113,19 @@ __device__ __forceinline__ bm_ray* output_rays(const FrameIO& io, uint32_t cur) 
 __device__ __forceinline__ uint32_t* output_mask(const FrameIO& io, uint32_t cur) { return cur ? io.mask[0] : io.mask[1]; }
 __device__ __forceinline__ const bm_ray* survivor_ptr(const SurvivorSet& io, uint32_t k) {
 	if (!io.in_prefix) return io.in + k;
-	uint32_t lo = 0, hi = io.ntiles;  // tile t = max{ t : prefix[t] <= k }
+	const uint32_t* base = io.in_prefix + io.ntiles + 1;
+	uint32_t blo = 0, bhi = scan_block_count(io.ntiles);  // scan block b = max{ b : base[b] <= k }
+	while (bhi - blo > 1) {
+		const uint32_t mid = (blo + bhi) >> 1;
+		if (__ldg(base + mid) <= k) blo = mid; else bhi = mid;
+	}
+	uint32_t r = k - __ldg(base + blo);
+	uint32_t lo = blo * kScanTiles, hi = min(io.ntiles, lo + kScanTiles);  // tile t = max{ t in the block : prefix[t] <= r }
 	while (hi - lo > 1) {
 		const uint32_t mid = (lo + hi) >> 1;
-		if (__ldg(io.in_prefix + mid) <= k) lo = mid; else hi = mid;
+		if (__ldg(io.in_prefix + mid) <= r) lo = mid; else hi = mid;
 	}
-	uint32_t r = k - __ldg(io.in_prefix + lo);
+	r -= __ldg(io.in_prefix + lo);
 	const uint32_t* m = io.in_mask + (size_t)lo * (kTile / 32);
 	uint32_t pos = 0;
 #pragma unroll
@@ -281,8 +294,7 @@ namespace bm {
 // set_wavefront_globals (kernel.cu:122-139) + per-tile survivor counts (popcount of the slot masks) -> exclusive prefix.
 // mask[ntiles * 8] -> prefix[ntiles + 1]; optional second pair for the shadow queue (RECORD). Also zeroes the mask buffer the NEXT
 // frame will write with atomicOr. Multi-block: block b scans kScanTiles tiles (one per thread) and leaves its total; the block that
-// finishes last (ticket counter, no waiting anywhere) scans the block totals, adds the bases and advances the frame state.
-constexpr int kScanTiles = 256;
+// finishes last (ticket counter, no waiting anywhere) scans the block totals into the block bases and advances the frame state.
 __device__ __forceinline__ uint32_t tile_count(const uint32_t* mask, uint32_t tile) {
 	const uint4 lo = *reinterpret_cast<const uint4*>(mask + (size_t)tile * 8), hi = *reinterpret_cast<const uint4*>(mask + (size_t)tile * 8 + 4);
 	return __popc(lo.x) + __popc(lo.y) + __popc(lo.z) + __popc(lo.w) + __popc(hi.x) + __popc(hi.y) + __popc(hi.z) + __popc(hi.w);
@@ -327,7 +339,7 @@ __global__ void __launch_bounds__(kScanTiles) scan_kernel(const FrameIO io, cons
 		const uint32_t n = tile < ntiles ? tile_count(in, tile) : 0u;
 		uint32_t total;
 		const uint32_t excl = block_exclusive_scan(n, s_warp, total);
-		if (tile < ntiles) out[tile] = excl;  // relative to the block; the last block adds the base
+		if (tile < ntiles) out[tile] = excl;  // relative to the scan block (see the prefix layout above)
 		if (threadIdx.x == 0) block_totals[pass * gridDim.x + blockIdx.x] = total;
 	}
 	if (tile < ntiles) {
@@ -352,15 +364,15 @@ __global__ void __launch_bounds__(kScanTiles) scan_kernel(const FrameIO io, cons
 			uint32_t chunk_total;
 			const uint32_t excl = block_exclusive_scan(v, s_warp, chunk_total);
 			const uint32_t carry = s_carry;
-			if (b < gridDim.x) totals[b] = carry + excl;
+			if (b < gridDim.x) out[ntiles + 1 + b] = carry + excl;  // survivors before scan block b
 			__syncthreads();
 			if (threadIdx.x == 0) s_carry = carry + chunk_total;
 			__syncthreads();
 		}
 		const uint32_t total = s_carry;
-		for (uint32_t t = kScanTiles + threadIdx.x; t < ntiles; t += kScanTiles) out[t] += totals[t / kScanTiles];  // (block 0's base is 0)
 		if (threadIdx.x == 0) {
 			out[ntiles] = total;
+			out[ntiles + 1 + gridDim.x] = total;
 			if (pass == 0) {
 				const uint32_t ran = st->n_active;                    // slots of the frame that just ran (n_slots unless BM_FRAME_EXACT_PATHS)
 				const uint32_t progress = ran - st->primary_ray_cnt;  // kernel.cu:125
@@ -412,7 +424,7 @@ __device__ __forceinline__ void export_tile(const T* src, const uint32_t* mask, 
 	if (!((word >> lane) & 1u)) return;
 	uint32_t rank = __popc(word & ((1u << lane) - 1u));
 	for (uint32_t k = 0; k < w; k++) rank += __popc(m[k]);
-	dst[prefix[tile] + rank] = src[(size_t)tile * kTile + threadIdx.x];
+	dst[prefix[ntiles + 1 + tile / kScanTiles] + prefix[tile] + rank] = src[(size_t)tile * kTile + threadIdx.x];
 }
 
 
@@ -423,7 +435,10 @@ __global__ void import_masks_kernel(uint32_t* mask, uint32_t* prefix, uint32_t n
 		const uint32_t first = i * 32;
 		mask[i] = count >= first + 32 ? 0xFFFFFFFFu : (count > first ? ((1u << (count - first)) - 1u) : 0u);
 	}
-	if (i <= ntiles) prefix[i] = min(i * (uint32_t)kTile, count);
+	const uint32_t per_block = (uint32_t)kScanTiles * kTile;  // slots per scan block
+	if (i < ntiles) prefix[i] = min(i * (uint32_t)kTile, count) - min((i / kScanTiles) * per_block, count);
+	if (i == ntiles) prefix[i] = count;
+	if (i <= scan_block_count(ntiles)) prefix[ntiles + 1 + i] = (uint32_t)min((unsigned long long)i * per_block, (unsigned long long)count);
 }
 
 // upload, kernel.cu:141-151, with the count read on the device (the reference copies it to the host first,
@@ -797,15 +812,15 @@ int bm_create(bm_context** out, const bm_config* cfg) {
 	for (int i = 0; i < 2; i++) {
 		CKC(cudaMalloc(&c->d_rays[i], (size_t)c->ntiles * kTile * sizeof(bm_ray)));
 		CKC(cudaMalloc(&c->d_mask[i], (size_t)c->ntiles * 32));
-		CKC(cudaMalloc(&c->d_prefix[i], (size_t)(c->ntiles + 1) * 4));
+		CKC(cudaMalloc(&c->d_prefix[i], prefix_words(c->ntiles) * 4));
 		CKC(cudaMemset(c->d_mask[i], 0, (size_t)c->ntiles * 32));
-		CKC(cudaMemset(c->d_prefix[i], 0, (size_t)(c->ntiles + 1) * 4));
+		CKC(cudaMemset(c->d_prefix[i], 0, prefix_words(c->ntiles) * 4));
 	}
 	CKC(cudaMalloc(&c->d_shadow_mask, (size_t)c->ntiles * 32));
 	CKC(cudaMemset(c->d_shadow_mask, 0, (size_t)c->ntiles * 32));
-	CKC(cudaMalloc(&c->d_shadow_prefix, (size_t)(c->ntiles + 1) * 4));
+	CKC(cudaMalloc(&c->d_shadow_prefix, prefix_words(c->ntiles) * 4));
 	CKC(cudaMalloc(&c->d_flag, 4));
-	c->scan_blocks = (c->ntiles + kScanTiles - 1) / kScanTiles;
+	c->scan_blocks = scan_block_count(c->ntiles);
 	CKC(cudaMalloc(&c->d_scan_totals, (size_t)c->scan_blocks * 8));
 	CKC(cudaMalloc(&c->d_scan_ticket, 4));
 	CKC(cudaMemset(c->d_scan_ticket, 0, 4));
@@ -1070,7 +1085,7 @@ static FrameIO private_io(bm_context* c, float* blit) {
 // no private survivor set (first frame, or after bm_set_counters without records): both sets empty, set 0 current
 static int clear_private_sets(bm_context* c) {
 	for (int i = 0; i < 2; i++) {
-		CK(cudaMemsetAsync(c->d_prefix[i], 0, (size_t)(c->ntiles + 1) * 4, c->stream));
+		CK(cudaMemsetAsync(c->d_prefix[i], 0, prefix_words(c->ntiles) * 4, c->stream));
 		CK(cudaMemsetAsync(c->d_mask[i], 0, (size_t)c->ntiles * 32, c->stream));
 	}
 	CK(cudaMemsetAsync(&c->d_state->cur, 0, 4, c->stream));

@@ -15,4 +15,5 @@ timeout 600 python bench.py > gpurun_out/${tag}_bench_ours.json 2> gpurun_out/${
 cat gpurun_out/${tag}_bench_ours.json
 timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file gpurun_out/${tag}_launches.csv python bench.py --steps 2 --warmup 3 --no-cpu-baseline > gpurun_out/${tag}_launches_bench.log 2>&1
 timeout 300 ncu --set full --clock-control none --import-source on -k regex:frame_kernel_q -s 10 -c 1 -f -o gpurun_out/${tag}_prof python tools/profile_frame.py > gpurun_out/${tag}_ncu.log 2>&1
+timeout 600 ncu --set full --clock-control none -k regex:frame_kernel_q -s 20 -c 1 -f -o gpurun_out/${tag}_prof_cfg4 python tools/profile_frame.py 24 cfg4 > gpurun_out/${tag}_ncu_cfg4.log 2>&1
 tail -2 gpurun_out/${tag}_ncu.log

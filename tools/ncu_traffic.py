@@ -17,7 +17,7 @@ config = sys.argv[2] if len(sys.argv) > 2 else "cfg3"
 raw = subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
 rows = list(csv.reader(io.StringIO(raw)))
 hdr, units = rows[0], rows[1]
-out = {"source_hash": source_hash(), "config": config, "report": os.path.basename(rep), "launches": []}
+out = {"report": os.path.basename(rep), "launches": []}
 for vals in rows[2:]:
     d = dict(zip(hdr, zip(units, vals)))
 
@@ -29,6 +29,17 @@ for vals in rows[2:]:
                             "duration_s": get("gpu__time_duration.sum")})
 l0 = out["launches"][0]
 out["dram_bytes_per_launch"] = l0["dram_bytes_read"] + l0["dram_bytes_write"]
-with open(os.path.join(ROOT, "profiles", "frame_kernel_traffic.json"), "w") as f:
-    json.dump(out, f, indent=1)
-print(json.dumps(out))
+if len(sys.argv) > 3:
+    out["rays_in_launch"] = float(sys.argv[3])  # (from the driver script's stats, for bytes per ray)
+path = os.path.join(ROOT, "profiles", "frame_kernel_traffic.json")
+try:
+    with open(path) as f:
+        allc = json.load(f)
+    if allc.get("source_hash") != source_hash() or "configs" not in allc:
+        allc = {"source_hash": source_hash(), "configs": {}}  # captures of other kernel sources do not describe this tree
+except Exception:
+    allc = {"source_hash": source_hash(), "configs": {}}
+allc["configs"][config] = out
+with open(path, "w") as f:
+    json.dump(allc, f, indent=1)
+print(json.dumps(allc))
