@@ -73,3 +73,31 @@ def test_spp_target_at_full_size(world):
     assert 4 * pixels <= st["terminations"] < 4 * pixels + cfg.ray_queue_buffer_size
     spp = blit[..., 3]
     assert spp.min().item() >= 2 and spp.max().item() <= 7  # the raster cursor spreads samples evenly (kernel.cu:170-171)
+
+
+def test_exact_paths_at_the_benchmark_size(world):
+    """bench.py's step at BASELINE config 3's full size: BM_FRAME_EXACT_PATHS gives every one of the 1920 x 1080 pixels exactly 16
+    finished paths, starts no ray beyond them, and two contexts on the two halves of the image (strips of 8 rows, as the multi-GPU
+    bench deals them) trace together exactly as many rays as one context on the whole image ... within the sampling noise of
+    different random sequences (their tiles seed differently): within 0.5 %."""
+    cfg, store = world
+    w, h = cfg.screen_width, cfg.screen_height
+    ren = new_renderer(cfg, store)
+    blit = torch.zeros(h, w, 4, dtype=torch.float32, device="cuda")
+    ren.render(blit, 200, target_paths=16 * w * h, flags=R.FRAME_EXACT_PATHS)
+    st = ren.stats()
+    assert st["terminations"] == 16 * w * h and ren.counters().primary_ray_cnt == 0
+    assert float(blit[..., 3].min()) == float(blit[..., 3].max()) == 16.0
+    assert torch.isfinite(blit).all()
+    total = 0
+    for rank in range(2):
+        rows, _ = bm.strip_rows_for_rank(h, rank, 2, 8)
+        c2 = bm.default_config(tile_rows=rows, strip_rows=8, strip_count=2, strip_index=rank)
+        r2 = bm.Renderer(c2, store)
+        r2.set_camera(bm.make_camera())
+        b2 = torch.zeros(rows, w, 4, dtype=torch.float32, device="cuda")
+        r2.render(b2, 200, target_paths=16 * rows * w, flags=R.FRAME_EXACT_PATHS)
+        s2 = r2.stats()
+        assert s2["terminations"] == 16 * rows * w and float(b2[..., 3].min()) == float(b2[..., 3].max()) == 16.0
+        total += s2["extend_rays"] + s2["shadow_rays"]
+    assert abs(total / (st["extend_rays"] + st["shadow_rays"]) - 1) < 0.005
