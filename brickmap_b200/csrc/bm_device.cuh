@@ -146,6 +146,12 @@ struct SceneView {
 	                              // bit (x'&3) | (y'&3)<<2 | (z'&3)<<4 of pair (z'>>2) * fine_nxy + (y'>>2) * fine_nx + (x'>>2); cells outside the
 	                              // world have their bit set. With coarse_shift == 2 the grid is the coarse bitmap's: fine_nx = 32 * coarse_roww
 	int fine_nx, fine_nxy;        // pairs per row / per slab
+	// "Open sky" table (library-private, built at bind time): for every column of (1 << sky_shift)^2 cells the highest z of a non-empty
+	// cell in the column grown by two cells on every side (-1: none). A ray that never descends (d.z >= 0) and is above these heights in
+	// every column it is still going to cross cannot meet a non-empty cell any more: it is a miss whatever its remaining DDA steps
+	// would have been (they change neither normal nor distance, voxel.cuh:199-247), so they are not taken. nullptr: test disabled.
+	const int16_t* sky;
+	int sky_shift, sky_n, sky_top;  // columns per axis; highest non-empty cell z of the world
 };
 
 struct WorkCounters {
@@ -452,6 +458,33 @@ __device__ __forceinline__ bool trace_setup(const SceneView& sv, F3 origin, cons
 	return true;
 }
 
+// Is the rest of this ray's way free of non-empty cells? Conservative, for rays that do not descend (integer step in z >= 0): a 2-D
+// DDA over the columns of SceneView::sky from the cell the ray stands in, with the cell-level DDA's own tmax / tdelta (column
+// crossing = cell crossing + the cells left to the column's edge). Margins: the table is grown by two cells sideways and the ray's
+// height at a column's entry is taken one cell lower than computed -- far more than the rounding drift of the DDA's accumulated
+// tmax (< 0.1 cell over 1500 steps). `p` is the UNBIASED cell position; t is measured along o + t d like tmax.
+__device__ __forceinline__ bool sky_clear(const SceneView& sv, const I3 p, const Dda& a, const float oz, const float dz) {
+	if ((unsigned)p.x >= (unsigned)sv.cells || (unsigned)p.y >= (unsigned)sv.cells || p.z < 0) return false;  // about to leave: the loop's business
+	if (p.z > sv.sky_top) return true;
+	const int sh = sv.sky_shift, edge = (1 << sh) - 1;
+	int cx = p.x >> sh, cy = p.y >> sh;
+	const float edge_f = (float)(1 << sh);
+	float tcx = a.stepi.x ? a.tmax.x + (float)(a.stepi.x > 0 ? edge - (p.x & edge) : (p.x & edge)) * a.tdelta.x : 3.0e38f;
+	float tcy = a.stepi.y ? a.tmax.y + (float)(a.stepi.y > 0 ? edge - (p.y & edge) : (p.y & edge)) * a.tdelta.y : 3.0e38f;
+	const float dcx = edge_f * a.tdelta.x, dcy = edge_f * a.tdelta.y;
+	int z = p.z;  // the ray never gets below the cell it stands in
+	for (int guard = 2 * sv.sky_n + 2; guard > 0; guard--) {
+		if (z <= (int)__ldg(sv.sky + cy * sv.sky_n + cx)) return false;
+		float t;
+		if (tcx < tcy) { t = tcx; cx += a.stepi.x; tcx += dcx; } else { t = tcy; cy += a.stepi.y; tcy += dcy; }
+		if (!(t < 1.0e30f)) return true;                                                           // never leaves this column sideways: it only rises in it
+		if ((unsigned)cx >= (unsigned)sv.sky_n || (unsigned)cy >= (unsigned)sv.sky_n) return true;  // leaves the world sideways
+		z = max(z, (int)floorf(fmaf(t, dz, oz)) - 1);
+		if (z > sv.sky_top) return true;
+	}
+	return false;
+}
+
 enum : int { TRACE_MISS = 0, TRACE_HIT = 1, TRACE_SUSPENDED = 2, TRACE_AT_BRICK = 3 };  // AT_BRICK: suspended in front of a cell whose brick is to be walked
 #ifndef BM_TRACE_CHUNK
 #define BM_TRACE_CHUNK 32
@@ -486,6 +519,9 @@ __device__ __forceinline__ int trace_run(const SceneView& sv, const uint32_t* co
 	// puts suspended rays into its queue and resumes them 32 at a time, so a thin warp is better given up early. Which lanes
 	// are "still here" is read with __activemask(): a heuristic only, suspending never changes a result.
 	for (int it = budget;;) {
+	// Before every chunk: can a ray that does not descend still meet anything? (Not in the work-counting pass, which counts the
+	// reference algorithm's steps.) The cell the ray stands in has not been tested yet: it is part of the question.
+	if (!COUNT && sv.sky && a.stepi.z >= 0 && sky_clear(sv, I3{ a.pos.x - bias, a.pos.y - bias, a.pos.z - bias }, a, origin.z, direction.z)) return TRACE_MISS;
 	for (int chunk = kTraceChunk; chunk > 0; chunk--) {
 		// Is the cell possibly non-empty? Shared-memory bitmap over blocks of cells first, then one bit per cell (global).
 		if (COUNT) wc->steps++;

@@ -552,6 +552,28 @@ __global__ void fine_build_kernel(const SceneView sv, uint32_t* fine, uint32_t n
 	fine[(size_t)b * 2 + 1] = hi;
 }
 
+// SceneView::sky, step 1: per cell column (x, y) the highest non-empty cell z, -1 if the column is empty
+__global__ void sky_cells_kernel(const SceneView sv, int16_t* cellmax) {
+	const int x = blockIdx.x * blockDim.x + threadIdx.x, y = blockIdx.y;
+	if (x >= sv.cells) return;
+	int top = -1;
+	for (int z = sv.cells_height - 1; z >= 0; z--) {
+		const int sc = (x >> 4) + (y >> 4) * sv.supergrid_xy + (z >> 4) * sv.supergrid_xy * sv.supergrid_xy;
+		if (sv.indices[sc][(x & 15) + (y & 15) * 16 + (z & 15) * 256]) { top = z; break; }
+	}
+	cellmax[(size_t)y * sv.cells + x] = (int16_t)top;
+}
+// step 2: per column of (1 << shift)^2 cells the maximum over the column grown by two cells on every side
+__global__ void sky_columns_kernel(const int16_t* cellmax, int cells, int shift, int n, int16_t* sky) {
+	const int c = blockIdx.x * blockDim.x + threadIdx.x;
+	if (c >= n * n) return;
+	const int cx = c % n, cy = c / n, side = 1 << shift;
+	int top = -1;
+	for (int y = max(0, cy * side - 2); y < min(cells, (cy + 1) * side + 2); y++)
+		for (int x = max(0, cx * side - 2); x < min(cells, (cx + 1) * side + 2); x++) top = max(top, (int)cellmax[(size_t)y * cells + x]);
+	sky[c] = (int16_t)top;
+}
+
 // is indices[sc] == indices[0] + sc * 4096 for every superchunk?
 __global__ void flat_check_kernel(uint32_t* const* indices, uint32_t n, uint32_t* not_flat) {
 	const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
@@ -635,6 +657,7 @@ struct bm_context {
 	SceneView sv{};
 	uint32_t* d_coarse = nullptr;
 	uint32_t* d_fine = nullptr;
+	int16_t* d_sky = nullptr;
 	uint32_t* d_flag = nullptr;
 	// host statics of launch_kernels (kernel.cu:367-382)
 	bm_camera cam{};
@@ -765,6 +788,7 @@ void bm_destroy(bm_context* c) {
 	cudaFree(c->d_state);
 	cudaFree(c->d_coarse);
 	cudaFree(c->d_fine);
+	cudaFree(c->d_sky);
 	cudaFree(c->d_flag);
 	cudaFree(c->d_scan_totals);
 	cudaFree(c->d_scan_ticket);
@@ -892,6 +916,38 @@ int bm_scene_bind(bm_context* c, bm_gpu_scene scene) {
 	fine_build_kernel<<<(nfine + 255) / 256, 256, 0, c->stream>>>(sv, c->d_fine, nfine);
 	CK(cudaGetLastError());
 	c->launches += 1;
+	// open-sky table (SceneView::sky): columns of 16 x 16 cells
+	sv.sky = nullptr;
+	sv.sky_shift = 4;
+	sv.sky_n = sv.cells >> sv.sky_shift;
+	sv.sky_top = sv.cells_height;
+	cudaFree(c->d_sky);
+	c->d_sky = nullptr;
+	{
+		int16_t* cellmax = nullptr;
+		CK(cudaMalloc(&cellmax, (size_t)sv.cells * sv.cells * sizeof(int16_t)));
+		CK(cudaMalloc(&c->d_sky, (size_t)sv.sky_n * sv.sky_n * sizeof(int16_t)));
+		sky_cells_kernel<<<dim3((sv.cells + 127) / 128, sv.cells), 128, 0, c->stream>>>(sv, cellmax);
+		CK(cudaGetLastError());
+		sky_columns_kernel<<<(sv.sky_n * sv.sky_n + 127) / 128, 128, 0, c->stream>>>(cellmax, sv.cells, sv.sky_shift, sv.sky_n, c->d_sky);
+		CK(cudaGetLastError());
+		std::vector<int16_t> h((size_t)sv.sky_n * sv.sky_n);
+		CK(cudaMemcpyAsync(h.data(), c->d_sky, h.size() * sizeof(int16_t), cudaMemcpyDeviceToHost, c->stream));
+		CK(cudaStreamSynchronize(c->stream));
+		CK(cudaFree(cellmax));
+		c->launches += 2;
+		int top = -1;
+		size_t open = 0;  // columns with at least two free cell layers above everything
+		for (int16_t v : h) {
+			top = v > top ? v : top;
+			open += v < sv.cells_height - 2;
+		}
+		sv.sky_top = top;
+		// worth testing only where there is sky: a world filled to the top (caves) would pay for tests that never succeed
+		bool enable = open * 8 >= h.size();
+		if (const char* e = getenv("BRICKMAP_B200_NO_SKY")) enable = enable && e[0] != '1';
+		if (enable) sv.sky = c->d_sky;
+	}
 	const uint32_t nsc = (uint32_t)(sv.supergrid_xy * sv.supergrid_xy * (sv.cells_height / 16));
 	CK(cudaMemsetAsync(c->d_flag, 0, 4, c->stream));
 	flat_check_kernel<<<(nsc + 255) / 256, 256, 0, c->stream>>>(scene.indices, nsc, c->d_flag);

@@ -291,10 +291,11 @@ def test_throughput_kernel_schedules_agree(golden, stores, variant, monkeypatch)
     cfg = store.cfg
     h, w = cfg.screen_height, cfg.screen_width
     results = []
-    for quantum, share, no_stock, descending, run_len, resume_at, brick_lanes in (
-            (64, 0, 0, 0, 1, 32, 0), (16, 0, 0, 0, 4, 32, 0), (256, 16, 0, 0, 1, 32, 0), (512, 28, 0, 1, 2, 24, 8), (256, 16, 1, 0, 1, 32, 0),
-            (128, 8, 0, 1, 16, 7, 32), (256, 18, 0, 0, 1, 24, 12), (64, 30, 0, 0, 1, 32, 32), (256, 18, 0, 0, 1, 24, 3), (32, 8, 1, 1, 8, 9, 5)):
+    for quantum, share, no_stock, descending, run_len, resume_at, brick_lanes, no_sky in (
+            (64, 0, 0, 0, 1, 32, 0, 1), (16, 0, 0, 0, 4, 32, 0, 0), (256, 16, 0, 0, 1, 32, 0, 0), (512, 28, 0, 1, 2, 24, 8, 1), (256, 16, 1, 0, 1, 32, 0, 0),
+            (128, 8, 0, 1, 16, 7, 32, 0), (256, 18, 0, 0, 1, 24, 12, 1), (64, 30, 0, 0, 1, 32, 32, 0), (256, 14, 0, 0, 1, 28, 3, 0), (32, 8, 1, 1, 8, 9, 5, 0)):
         monkeypatch.setenv("BRICKMAP_B200_BRICK_LANES", str(brick_lanes))
+        monkeypatch.setenv("BRICKMAP_B200_NO_SKY", str(no_sky))  # 1: without the early "nothing left to meet" exit of non-descending rays
         monkeypatch.setenv("BRICKMAP_B200_RUN_LEN", str(run_len))
         monkeypatch.setenv("BRICKMAP_B200_RESUME_AT", str(resume_at))
         monkeypatch.setenv("BRICKMAP_B200_QUANTUM", str(quantum))
