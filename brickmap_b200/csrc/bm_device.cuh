@@ -463,7 +463,9 @@ __device__ __forceinline__ bool trace_setup(const SceneView& sv, F3 origin, cons
 // crossing = cell crossing + the cells left to the column's edge). Margins: the table is grown by two cells sideways and the ray's
 // height at a column's entry is taken one cell lower than computed -- far more than the rounding drift of the DDA's accumulated
 // tmax (< 0.1 cell over 1500 steps). `p` is the UNBIASED cell position; t is measured along o + t d like tmax.
-__device__ __forceinline__ bool sky_clear(const SceneView& sv, const I3 p, const Dda& a, const float oz, const float dz) {
+// On "no" `retry_after` receives the time at which the ray leaves the column that blocks it: asking again before that gives the same
+// answer (the column's entry height is a function of the ray alone).
+__device__ __forceinline__ bool sky_clear(const SceneView& sv, const I3 p, const Dda& a, const float oz, const float dz, float& retry_after) {
 	if ((unsigned)p.x >= (unsigned)sv.cells || (unsigned)p.y >= (unsigned)sv.cells || p.z < 0) return false;  // about to leave: the loop's business
 	if (p.z > sv.sky_top) return true;
 	const int sh = sv.sky_shift, edge = (1 << sh) - 1;
@@ -474,7 +476,10 @@ __device__ __forceinline__ bool sky_clear(const SceneView& sv, const I3 p, const
 	const float dcx = edge_f * a.tdelta.x, dcy = edge_f * a.tdelta.y;
 	int z = p.z;  // the ray never gets below the cell it stands in
 	for (int guard = 2 * sv.sky_n + 2; guard > 0; guard--) {
-		if (z <= (int)__ldg(sv.sky + cy * sv.sky_n + cx)) return false;
+		if (z <= (int)__ldg(sv.sky + cy * sv.sky_n + cx)) {
+			retry_after = fminf(tcx, tcy);
+			return false;
+		}
 		float t;
 		if (tcx < tcy) { t = tcx; cx += a.stepi.x; tcx += dcx; } else { t = tcy; cy += a.stepi.y; tcy += dcy; }
 		if (!(t < 1.0e30f)) return true;                                                           // never leaves this column sideways: it only rises in it
@@ -518,10 +523,13 @@ __device__ __forceinline__ int trace_run(const SceneView& sv, const uint32_t* co
 	// or if fewer than `min_lanes` lanes of the warp are still tracing (the others have finished their rays and wait): the caller
 	// puts suspended rays into its queue and resumes them 32 at a time, so a thin warp is better given up early. Which lanes
 	// are "still here" is read with __activemask(): a heuristic only, suspending never changes a result.
+	float sky_retry = -1.f;  // (tmax is never negative: the first question is always asked)
 	for (int it = budget;;) {
 	// Before every chunk: can a ray that does not descend still meet anything? (Not in the work-counting pass, which counts the
 	// reference algorithm's steps.) The cell the ray stands in has not been tested yet: it is part of the question.
-	if (!COUNT && sv.sky && a.stepi.z >= 0 && sky_clear(sv, I3{ a.pos.x - bias, a.pos.y - bias, a.pos.z - bias }, a, origin.z, direction.z)) return TRACE_MISS;
+	if (!COUNT && sv.sky && a.stepi.z >= 0 && fminf(fminf(a.tmax.x, a.tmax.y), a.tmax.z) > sky_retry &&
+	    sky_clear(sv, I3{ a.pos.x - bias, a.pos.y - bias, a.pos.z - bias }, a, origin.z, direction.z, sky_retry))
+		return TRACE_MISS;
 	for (int chunk = kTraceChunk; chunk > 0; chunk--) {
 		// Is the cell possibly non-empty? Shared-memory bitmap over blocks of cells first, then one bit per cell (global).
 		if (COUNT) wc->steps++;

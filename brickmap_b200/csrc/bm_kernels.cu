@@ -678,7 +678,7 @@ struct bm_context {
 	// throughput kernel (frame_kernel_q)
 	bool use_quantum = true;  // BRICKMAP_B200_SIMPLE_KERNEL=1 switches the throughput path back to frame_kernel
 	int quantum = 256;        // BRICKMAP_B200_QUANTUM: cell tests per lane and batch at most (with min_share 16: 64 -> 2440, 128 -> 2478, 256 -> 2494 Mrays/s)
-	int min_share = 14;       // BRICKMAP_B200_MIN_SHARE: a batch is given up when fewer than min_share / 32 of its tracing lanes are left (profiles/r2_o_sweep_chunk32.txt)
+	int min_share = 10;       // BRICKMAP_B200_MIN_SHARE: a batch is given up when fewer than min_share / 32 of its tracing lanes are left (profiles/r2_o_sweep_chunk32.txt, r2_u_sweep_sky_columns.txt)
 	int run_len = 1;          // BRICKMAP_B200_RUN_LEN (1: 2723, 2: 2666, 4: 2503, 8: 2215, 16: 1683 Mrays/s -- the runs a warp still holds when the pool runs dry are the frame's tail)
 	int resume_at = 28;       // BRICKMAP_B200_RESUME_AT (profiles/r2_j_sweep_resume_at.txt, r2_o_sweep_chunk32.txt)
 	int brick_lanes = 3;      // BRICKMAP_B200_BRICK_LANES (0: 3089, 2: 3184, 3: 3200, 4: 3192, 6: 3157, 10: 3031, 16: 2886 Mrays/s): bricks reached by fewer lanes than this suspend the ray in front of the brick (0: never)
@@ -919,6 +919,7 @@ int bm_scene_bind(bm_context* c, bm_gpu_scene scene) {
 	// open-sky table (SceneView::sky): columns of 16 x 16 cells
 	sv.sky = nullptr;
 	sv.sky_shift = 4;
+	if (const char* e = getenv("BRICKMAP_B200_SKY_SHIFT")) sv.sky_shift = atoi(e) >= 1 && atoi(e) <= 6 ? atoi(e) : sv.sky_shift;  // columns of 2^shift cells (tuning)
 	sv.sky_n = sv.cells >> sv.sky_shift;
 	sv.sky_top = sv.cells_height;
 	cudaFree(c->d_sky);
