@@ -22,7 +22,7 @@ def source_hash():
     """sha256 (first 12 hex digits) over the kernel sources: stamps measurements that describe one build (profiles/frame_kernel_traffic.json)."""
     import hashlib
     h = hashlib.sha256()
-    for name in sorted(SOURCES + HEADERS):
+    for name in sorted(n for n in SOURCES + HEADERS if not n.startswith("..")):  # csrc/ only: the public header's comments do not change a kernel
         with open(os.path.join(CSRC, name), "rb") as f:
             h.update(f.read())
     return h.hexdigest()[:12]

@@ -135,8 +135,9 @@ void bm_destroy(bm_context* ctx);
 const char* bm_last_error_string(void);
 
 /* Bind the scene handle (the GPUScene that launch_kernels receives by value, launch.h:6). Builds the derived,
- * library-private traversal aids from it: an emptiness bitmap over blocks of cells (a cell is empty iff its
- * index word is 0, which streaming never changes: Scene.cpp:158-164, kernel.cu:150) and a check whether the
+ * library-private traversal aids from it: emptiness bitmaps over blocks of cells and per cell (a cell is empty iff its
+ * index word is 0, which streaming never changes: Scene.cpp:158-164, kernel.cu:150), the per-column tops of the non-empty
+ * cells (rays that cannot meet anything any more are ended as the misses they are) and a check whether the
  * per-superchunk index arrays form one flat arena. Must be called again only if the SET of empty cells or
  * the pointer tables' index-array entries change; brick arrays may be re-allocated freely (Scene.cpp:242-246),
  * they are always reached through the table. */
