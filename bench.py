@@ -571,7 +571,7 @@ def main():
     achieved = (bytes_per_ray * rays_per_launch) / (kernel_ms / launches0 * 1e-3) / 1e9 if (kernel_ms > 0 and bytes_per_ray) else None
     # DRAM traffic of the kernel: an ncu capture (tools/gpu_round.sh writes profiles/frame_kernel_traffic.json, stamped with the commit
     # and the config it was taken on); a capture of another tree, another config or another GPU count does not describe this run
-    traffic, traffic_note = None, "no ncu capture for this tree / config / GPU count"
+    traffic, traffic_note, traffic_steady = None, "no ncu capture for this tree / config / GPU count", None
     try:
         from brickmap_b200.build import source_hash
         with open(os.path.join(ROOT, "profiles", "frame_kernel_traffic.json")) as f:
@@ -579,6 +579,7 @@ def main():
         entry = (tj.get("configs") or {}).get(args.config)
         if entry and tj.get("source_hash") == source_hash() and world == 1:
             traffic, traffic_note = entry.get("dram_bytes_per_launch"), "ncu --set full capture of one launch of these kernel sources (hash %s), %s" % (tj["source_hash"], entry.get("report"))
+            traffic_steady = (entry.get("steady") or {}).get("dram_bytes_per_launch")
         elif entry and world == 1:
             traffic_note = "the committed capture describes kernel sources %s, this tree is %s" % (tj.get("source_hash"), source_hash())
     except Exception:
@@ -588,6 +589,11 @@ def main():
                 "algorithmic_bytes_per_ray": bytes_per_ray, "rays_per_launch": rays_per_launch, "kernel_ms_per_launch": kernel_ms / launches0,
                 "kernel_share_of_step": kernel_ms / ms if ms > 0 else None,
                 "traffic_bytes_per_ray": (traffic / rays_per_launch) if traffic else None, "per_ray": per_ray}
+    if traffic_steady:
+        # the --set full capture flushes the L2 before every replay pass; this is the same kernel's DRAM traffic per launch in a second,
+        # single-pass capture of consecutive launches without that flush (the state the timed launches run in)
+        roofline.update(traffic_steady=traffic_steady, traffic_steady_bytes_per_ray=traffic_steady / rays_per_launch,
+                        traffic_steady_note="ncu single pass, --cache-control none, mean of consecutive launches of the same sources")
     if primary_only:
         roofline["note"] = "primary rays only: the work counters are not collected (they live in the shading kernels); the 64-byte result record per ray is the output"
     cpu = None if args.no_cpu_baseline else cpu_baseline_port(conf)

@@ -868,4 +868,88 @@ __device__ __forceinline__ void store_ray(bm_ray* p, const Ray& r) {
 	q[3] = make_float4(r.distance, __int_as_float(r.identifier), __int_as_float(r.bounces), __uint_as_float(r.pixel_index));
 }
 
+// L2 residency of the PRIVATE survivor sets of frame_kernel_q (bm_render). A survivor record is written once (frame f), read once
+// (frame f + 1) and dead from then on. Left to the cache's own replacement that round trip -- 0.95 M records x 64 B per frame, written
+// back and fetched again -- plus the dead lines it leaves behind is most of the kernel's DRAM traffic, although the live set (61 MB)
+// is half of the B200's L2. BM_SURV_HINTS is a bit set (compile time); measured same-box, steady state (ncu single pass, no cache
+// flush, mean of three launches of the benchmark view; profiles/r2_w_surv_hints.txt), default 6:
+//   0   nothing:                                                        101 MB read + 98 MB written per launch, 0.763 ms per frame
+//   2   the write carries an L2 evict_last policy (createpolicy + st.global.L2::cache_hint): the line should still be there when read
+//   4   after the read the 128-byte line is dropped from L2 WITHOUT a write-back (discard.global.L2; SASS CCTL.E.RML2) -- done only when
+//       both records of the line have been read by the same warp or the other half holds no survivor (frame_kernel_q)
+//   6   both:                                                            53 MB read + 65 MB written, 0.758 ms (4 alone: 55 + 89)
+//   1 / 64  streaming read (ld.global.cs) / L2 evict_first read: no less traffic than 6 (7: 54 + 65; 70: 53 + 67), 2 % slower
+//   8   streaming write (st.global.cs) instead of 2 (9: 68 + 77; 28: 52 + 60)
+//   16  the accumulation reduction carries evict_last as well (22: 54 + 64: no gain; 20: 52 + 63)
+//   128 MEASUREMENT ONLY, wrong images: no accumulation (attributes the traffic: 59 MB of the 199 and 61 of the 118 are the image's)
+// Cache hints cannot change a result; the drop could (a record dropped before it is read is garbage) and is covered by every
+// multi-frame parity test.
+#ifndef BM_SURV_HINTS
+#define BM_SURV_HINTS 6
+#endif
+#ifndef BM_SURV_FRACTION
+#define BM_SURV_FRACTION "1.0"  // share of the survivor stores that carry evict_last (0.5: 51 + 64 MB, no gain)
+#endif
+__device__ __forceinline__ Ray load_ray_private(const bm_ray* p, uint32_t& witness) {
+#if BM_SURV_HINTS & 1
+	float4 a, b, c, d;
+	asm volatile("ld.global.cs.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(a.x), "=f"(a.y), "=f"(a.z), "=f"(a.w) : "l"(p));
+	asm volatile("ld.global.cs.v4.f32 {%0, %1, %2, %3}, [%4 + 16];" : "=f"(b.x), "=f"(b.y), "=f"(b.z), "=f"(b.w) : "l"(p));
+	asm volatile("ld.global.cs.v4.f32 {%0, %1, %2, %3}, [%4 + 32];" : "=f"(c.x), "=f"(c.y), "=f"(c.z), "=f"(c.w) : "l"(p));
+	asm volatile("ld.global.cs.v4.f32 {%0, %1, %2, %3}, [%4 + 48];" : "=f"(d.x), "=f"(d.y), "=f"(d.z), "=f"(d.w) : "l"(p));
+#elif BM_SURV_HINTS & 64
+	float4 a, b, c, d;  // evict_first in L2 only (L1 behaviour unchanged)
+	unsigned long long pol;
+	asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(pol));
+	asm volatile("ld.global.L2::cache_hint.v4.f32 {%0, %1, %2, %3}, [%4], %5;" : "=f"(a.x), "=f"(a.y), "=f"(a.z), "=f"(a.w) : "l"(p), "l"(pol));
+	asm volatile("ld.global.L2::cache_hint.v4.f32 {%0, %1, %2, %3}, [%4 + 16], %5;" : "=f"(b.x), "=f"(b.y), "=f"(b.z), "=f"(b.w) : "l"(p), "l"(pol));
+	asm volatile("ld.global.L2::cache_hint.v4.f32 {%0, %1, %2, %3}, [%4 + 32], %5;" : "=f"(c.x), "=f"(c.y), "=f"(c.z), "=f"(c.w) : "l"(p), "l"(pol));
+	asm volatile("ld.global.L2::cache_hint.v4.f32 {%0, %1, %2, %3}, [%4 + 48], %5;" : "=f"(d.x), "=f"(d.y), "=f"(d.z), "=f"(d.w) : "l"(p), "l"(pol));
+#else
+	const float4* q = reinterpret_cast<const float4*>(p);
+	const float4 a = q[0], b = q[1], c = q[2], d = q[3];
+#endif
+	// a value that exists only once all four loads have returned (the discard waits for it, across lanes through a shuffle)
+	witness = __float_as_uint(a.x) ^ __float_as_uint(b.x) ^ __float_as_uint(c.x) ^ __float_as_uint(d.x);
+	Ray r;
+	r.origin = F3{ a.x, a.y, a.z };
+	r.direction = F3{ a.w, b.x, b.y };
+	r.throughput = F3{ b.z, b.w, c.x };
+	r.normal = F3{ c.y, c.z, c.w };
+	r.distance = d.x;
+	r.identifier = __float_as_int(d.y);
+	r.bounces = __float_as_int(d.z);
+	r.pixel_index = __float_as_uint(d.w);
+	return r;
+}
+__device__ __forceinline__ void store_ray_private(bm_ray* p, const Ray& r) {
+#if BM_SURV_HINTS & 2
+	asm volatile(
+	    "{\n\t"
+	    ".reg .b64 pol;\n\t"
+	    "createpolicy.fractional.L2::evict_last.b64 pol, " BM_SURV_FRACTION ";\n\t"
+	    "st.global.L2::cache_hint.v4.f32 [%0], {%1, %2, %3, %4}, pol;\n\t"
+	    "st.global.L2::cache_hint.v4.f32 [%0 + 16], {%5, %6, %7, %8}, pol;\n\t"
+	    "st.global.L2::cache_hint.v4.f32 [%0 + 32], {%9, %10, %11, %12}, pol;\n\t"
+	    "st.global.L2::cache_hint.v4.f32 [%0 + 48], {%13, %14, %15, %16}, pol;\n\t"
+	    "}" ::"l"(p),
+	    "f"(r.origin.x), "f"(r.origin.y), "f"(r.origin.z), "f"(r.direction.x), "f"(r.direction.y), "f"(r.direction.z), "f"(r.throughput.x), "f"(r.throughput.y),
+	    "f"(r.throughput.z), "f"(r.normal.x), "f"(r.normal.y), "f"(r.normal.z), "f"(r.distance), "f"(__int_as_float(r.identifier)), "f"(__int_as_float(r.bounces)),
+	    "f"(__uint_as_float(r.pixel_index))
+	    : "memory");
+#elif BM_SURV_HINTS & 8
+	asm volatile(
+	    "st.global.cs.v4.f32 [%0], {%1, %2, %3, %4};\n\t"
+	    "st.global.cs.v4.f32 [%0 + 16], {%5, %6, %7, %8};\n\t"
+	    "st.global.cs.v4.f32 [%0 + 32], {%9, %10, %11, %12};\n\t"
+	    "st.global.cs.v4.f32 [%0 + 48], {%13, %14, %15, %16};" ::"l"(p),
+	    "f"(r.origin.x), "f"(r.origin.y), "f"(r.origin.z), "f"(r.direction.x), "f"(r.direction.y), "f"(r.direction.z), "f"(r.throughput.x), "f"(r.throughput.y),
+	    "f"(r.throughput.z), "f"(r.normal.x), "f"(r.normal.y), "f"(r.normal.z), "f"(r.distance), "f"(__int_as_float(r.identifier)), "f"(__int_as_float(r.bounces)),
+	    "f"(__uint_as_float(r.pixel_index))
+	    : "memory");
+#else
+	store_ray(p, r);
+#endif
+}
+
 }  // namespace bm

@@ -177,10 +177,22 @@ __global__ void __launch_bounds__(kQBlock, 1) frame_kernel_q(const FrameParams f
 			}
 			slot = (run * kRun + round) * 32 + lane;
 			round++;
+			const bm_ray* mine = nullptr;  // the private survivor record this lane reads (BM_SURV_HINTS)
+			uint32_t witness = 0;
 			if (slot < n_slots) {
 				Ray ray;
-				if (slot < c) ray = load_ray(survivor_ptr(input_set(io, cur), slot));
-				else ray = generate_primary(fp, frame, start, slot - c);  // primary_rays, kernel.cu:154-223
+				if (slot < c) {
+					const SurvivorSet in = input_set(io, cur);
+					const bm_ray* p = survivor_ptr(in, slot);
+					if (BM_SURV_HINTS && !RECORD && in.in_prefix) {
+						ray = load_ray_private(p, witness);
+						mine = p;
+					} else {
+						ray = load_ray(p);
+					}
+				} else {
+					ray = generate_primary(fp, frame, start, slot - c);  // primary_rays, kernel.cu:154-223
+				}
 				kind = K_EXTEND;
 				world = ray.origin;
 				direction = ray.direction;
@@ -190,6 +202,37 @@ __global__ void __launch_bounds__(kQBlock, 1) frame_kernel_q(const FrameParams f
 				bounces = ray.bounces;
 				tracing = trace_setup(sv, ray.origin, ray.direction, normal, ts);  // extend, kernel.cu:226-238
 			}
+#if BM_SURV_HINTS & 4
+			if (!RECORD) {
+				// Drop the lines just read from L2 without a write-back: the records are dead (a set is read once, by the frame after the one
+				// that wrote it). A 128-byte line holds the records of slots 2j and 2j + 1 of the sparse set. Two survivors that share a line
+				// are consecutive survivors, i.e. in neighbouring lanes -- unless a warp boundary falls between them. The lane holding the
+				// even slot drops the line when the odd one was read by the next lane; either lane drops it when the other half holds no
+				// survivor (mask bit clear); a line split between two warps is left to the normal eviction. The shuffle of `witness` makes
+				// the drop wait for the loads of BOTH lanes (the shuffle cannot issue before every lane's loads have returned).
+				const unsigned long long a = (unsigned long long)mine;
+				const unsigned long long up = __shfl_down_sync(0xFFFFFFFFu, a, 1);
+				const uint32_t w_up = __shfl_down_sync(0xFFFFFFFFu, witness, 1);
+				bool drop = false;
+				if (mine) {
+					const SurvivorSet in = input_set(io, cur);
+					const size_t s = (size_t)(mine - in.in), other = s ^ 1;
+					if (!(s & 1) && lane < 31 && up == a + sizeof(bm_ray)) drop = true;
+					else drop = !((__ldg(in.in_mask + (other >> 5)) >> (other & 31)) & 1u);
+				}
+				// (a real use of both witnesses: the drop is predicated on their xor not being one particular value -- skipping a drop is harmless)
+				if (drop)
+					asm volatile(
+					    "{\n\t"
+					    ".reg .pred p;\n\t"
+					    ".reg .b32 t;\n\t"
+					    "xor.b32 t, %1, %2;\n\t"
+					    "setp.ne.u32 p, t, 0x9E3779B9;\n\t"
+					    "@p discard.global.L2 [%0], 128;\n\t"
+					    "}" ::"l"(a & ~127ull), "r"(witness), "r"(w_up)
+					    : "memory");
+			}
+#endif
 		} else {
 			break;
 		}
@@ -238,7 +281,8 @@ __global__ void __launch_bounds__(kQBlock, 1) frame_kernel_q(const FrameParams f
 				else if (s.terminated) accum_add(io.accum, pixel, 0.f, 0.f, 0.f, 1.f);
 				n_term += s.terminated;
 				if (s.survives) {
-					store_ray(output_rays(io, cur) + slot, ray);
+					if (BM_SURV_HINTS && !RECORD) store_ray_private(output_rays(io, cur) + slot, ray);
+					else store_ray(output_rays(io, cur) + slot, ray);
 					atomicOr(output_mask(io, cur) + (slot >> 5), 1u << (slot & 31));
 				}
 				if (s.has_shadow) {

@@ -86,7 +86,22 @@ struct FrameIO {
 
 __device__ __forceinline__ void accum_add(float4* accum, uint32_t pixel, float r, float g, float b, float a) {
 	// one 128-bit reduction instead of the reference's 3-4 scalar float atomics (kernel.cu:319-322,341-343)
+#if BM_SURV_HINTS & 128
+	// MEASUREMENT BUILD ONLY (wrong images): no accumulation at all -- the rays are the same ones (nothing reads the image back), so the
+	// difference in DRAM traffic to the normal build is the accumulation buffer's share (profiles/r2_w_*)
+	(void)accum; (void)pixel; (void)r; (void)g; (void)b; (void)a;
+#elif BM_SURV_HINTS & 16
+	// ... carrying an L2 evict_last policy: the image (33 MB at 1080p) is touched all over by every frame and should outlive the survivor streams
+	asm volatile(
+	    "{\n\t"
+	    ".reg .b64 pol;\n\t"
+	    "createpolicy.fractional.L2::evict_last.b64 pol, 1.0;\n\t"
+	    "red.global.add.L2::cache_hint.v4.f32 [%0], {%1, %2, %3, %4}, pol;\n\t"
+	    "}" ::"l"(accum + pixel), "f"(r), "f"(g), "f"(b), "f"(a)
+	    : "memory");
+#else
 	atomicAdd(accum + pixel, make_float4(r, g, b, a));
+#endif
 }
 
 // Where is survivor number `k` of the previous frame? Stable compaction = the reference's atomicAdd(&primary_ray_cnt, 1)

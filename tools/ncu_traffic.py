@@ -1,6 +1,9 @@
 """DRAM traffic of one frame-kernel launch from an ncu --set full capture -> profiles/frame_kernel_traffic.json (read by bench.py as
 roofline.traffic). Stamped with a hash of the kernel sources and the bench config it was taken on: bench.py reports traffic only
-when both match the tree and config it runs.   usage: python tools/ncu_traffic.py gpurun_out/<tag>_prof.ncu-rep [config=cfg3]"""
+when both match the tree and config it runs.   usage: python tools/ncu_traffic.py gpurun_out/<tag>_prof.ncu-rep [config=cfg3] [rays|-] [steady.csv]
+steady.csv: the log of a second, single-pass capture of consecutive launches WITHOUT ncu's cache flush (--cache-control none --metrics
+dram__bytes_read.sum,dram__bytes_write.sum,gpu__time_duration.sum --csv): what a launch moves when its predecessor's L2 contents are still
+there (the --set full capture flushes the L2 before every replay pass, so the survivors the previous frame left in L2 are gone)."""
 import csv
 import io
 import json
@@ -29,8 +32,20 @@ for vals in rows[2:]:
                             "duration_s": get("gpu__time_duration.sum")})
 l0 = out["launches"][0]
 out["dram_bytes_per_launch"] = l0["dram_bytes_read"] + l0["dram_bytes_write"]
-if len(sys.argv) > 3:
+if len(sys.argv) > 3 and sys.argv[3] != "-":
     out["rays_in_launch"] = float(sys.argv[3])  # (from the driver script's stats, for bytes per ray)
+if len(sys.argv) > 4:
+    per = {}
+    with open(sys.argv[4]) as f:
+        lines = [l for l in f if not l.startswith("==")]
+    for r in csv.DictReader(lines):
+        v = float(r["Metric Value"].replace(",", ""))
+        v *= {"Gbyte": 1e9, "Mbyte": 1e6, "Kbyte": 1e3, "byte": 1.0}.get(r["Metric Unit"], 1.0)
+        if r["Metric Name"].startswith("dram__bytes"):
+            per[r["ID"]] = per.get(r["ID"], 0.0) + v
+    if per:
+        out["steady"] = {"log": os.path.basename(sys.argv[4]), "launches": len(per), "dram_bytes_per_launch": sum(per.values()) / len(per),
+                         "method": "ncu single pass, --cache-control none, consecutive steady-state launches (mean)"}
 path = os.path.join(ROOT, "profiles", "frame_kernel_traffic.json")
 try:
     with open(path) as f:
