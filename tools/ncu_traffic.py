@@ -45,6 +45,7 @@ if len(sys.argv) > 4:
             per[r["ID"]] = per.get(r["ID"], 0.0) + v
     if per:
         out["steady"] = {"log": os.path.basename(sys.argv[4]), "launches": len(per), "dram_bytes_per_launch": sum(per.values()) / len(per),
+                         "dram_bytes_of_each_launch": [per[k] for k in sorted(per, key=int)],
                          "method": "ncu single pass, --cache-control none, consecutive steady-state launches (mean)"}
 path = os.path.join(ROOT, "profiles", "frame_kernel_traffic.json")
 try:

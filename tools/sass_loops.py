@@ -61,3 +61,19 @@ b_end = find(r"BRA", shf[-1])
 tgt = int(re.search(r"BRA 0x([0-9a-f]+)", lines[b_end]).group(1), 16)
 b_start = [i for i in range(len(lines)) if addr(i) == tgt][0]
 show("brick walk (intersect_brick, one block of PTX): one voxel step incl. exit test, z-slice reload, bit test", b_start, b_end)
+# survivor records: stores that carry the L2 evict_last policy (the descriptor is built in uniform registers right before) and the drop
+# of a line after both of its records have been read (discard.global.L2 -> CCTL.E.RML2)
+stg = [i for i in range(len(lines)) if re.search(r"STG\.E\.128", lines[i])]
+if stg:
+    first = stg[0]
+    pol = [i for i in range(max(0, first - 30), first) if re.search(r"UMOV UR\d+, 0x(f0|140)|ULOP3|USHF", lines[i])]
+    print("== survivor store with the L2 evict_last policy (createpolicy -> descriptor 0x14f0... in UR; BM_SURV_HINTS & 2)")
+    for i in pol + stg[:4]:
+        print("    " + lines[i])
+    print()
+rml = [i for i in range(len(lines)) if "CCTL.E.RML2" in lines[i]]
+if rml:
+    print("== drop of a dead survivor line from L2 without a write-back (discard.global.L2; BM_SURV_HINTS & 4)")
+    for i in range(rml[0] - 3, rml[0] + 1):
+        print("    " + lines[i])
+    print()
