@@ -1,0 +1,9 @@
+#!/bin/bash
+# compute-sanitizer memcheck only (the shipped tree's discard / cache-hint paths): smoke() and the multi-frame bm_render tests
+tag=${1:-x}
+mkdir -p gpurun_out
+CS=/usr/local/cuda/bin/compute-sanitizer
+timeout 100 $CS --tool memcheck --print-limit 20 python -c "import __graft_entry__ as g; g.smoke()" > gpurun_out/${tag}_sanitizer_memcheck_smoke.log 2>&1
+echo "memcheck smoke rc=$?"; grep -E "ERROR SUMMARY|smoke ok" gpurun_out/${tag}_sanitizer_memcheck_smoke.log | tail -3
+timeout 100 $CS --tool memcheck --print-limit 20 python -m pytest tests/test_gpu_parity.py -m gpu -q -x -k "test_streaming_matches_oracle_as_sets or test_multi_frame_render_uploads_once or test_render_target_slack" > gpurun_out/${tag}_sanitizer_memcheck_streaming.log 2>&1
+echo "memcheck streaming rc=$?"; grep -E "ERROR SUMMARY|passed|failed" gpurun_out/${tag}_sanitizer_memcheck_streaming.log | tail -3
