@@ -204,7 +204,7 @@ def cpu_baseline_port(conf, frames=3):
     rays = ren.stats.rays
     out = {"value": rays / dt / 1e6, "unit": "Mrays/s", "cores": cores, "kind": "port",
            "sample": "%s (%d rays); extend and connect (the traversal, >95%% of the scalar work) multi-threaded over all cores, "
-                     "ray generation threaded too, the shade loop single-threaded in slot order (the canonical compaction order is sequential)" % (what, rays),
+                     "ray generation and the per-slot shading work threaded too; only the append of survivor / shadow records and the accumulation run sequentially, in slot order (the canonical compaction order)" % (what, rays),
            "seconds": dt}
     if conf["scene"] != "caves" and not conf.get("primary_only"):
         # untimed: one more frame with the footprint instrumentation on -> minimum brick-index footprint (32 B x unique
